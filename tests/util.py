@@ -1,0 +1,47 @@
+"""Shared helpers for the parity tests."""
+import os
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+_cache = {}
+
+
+def golden(name):
+    if name not in _cache:
+        with np.load(os.path.join(GOLDEN, name + '.npz')) as z:
+            _cache[name] = {k: z[k] for k in z.files}
+    return _cache[name]
+
+
+def T(a, device='cpu'):
+    return torch.from_numpy(np.asarray(a)).to(device)
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|_inf, tiny): the '1e-4 relative in fp32' bar of BASELINE.json is read as
+    error relative to the tensor's scale (per-element relative error is meaningless at zero crossings)."""
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(b.abs().max().item(), 1e-30)
+    return (a - b).abs().max().item() / scale
+
+
+def assert_close(a, b, tol=1e-4, what=''):
+    e = rel_err(a, b)
+    assert e <= tol, f'{what}: rel err {e:.3e} > {tol:.1e}'
+
+
+def key_with_stride(d, prefix):
+    """Golden grads of big tensors are stored as flat[::stride] under 'name@stride'."""
+    for k in d:
+        if k == prefix:
+            return k, None
+        if k.startswith(prefix + '@'):
+            return k, int(k.split('@')[1])
+    raise KeyError(prefix)
+
+
+def pick(g, stride):
+    return g if stride is None else g.flatten()[::stride]

@@ -1,0 +1,62 @@
+// ccb_common.cuh - shared host/device helpers for libccb200 (sm_100a).
+#pragma once
+#include "../../include/ccb200.h"
+
+#ifdef CCB_CPU_SIM
+#include "cusim.h"   // tests/sim: CPU execution-model simulator, TEST BUILDS ONLY
+#else
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#define CCB_LAUNCH(kern, grid, block, smem, stream, ...) \
+    kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define CCB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+namespace ccb {
+
+// ---- error plumbing (C ABI never throws; reference raises AssertionError in Python instead) ----
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define CCB_REQUIRE(cond, code, ...)            \
+    do {                                        \
+        if (!(cond)) {                          \
+            ccb::set_error(__VA_ARGS__);        \
+            return (code);                      \
+        }                                       \
+    } while (0)
+
+// ---- small device helpers ----
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum of NV values per thread; result valid in thread 0.  `scratch` holds >= NV*32 floats.
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) scratch[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float x = (lane < nwarps) ? scratch[i * 32 + lane] : 0.f;
+            v[i] = warp_sum(x);
+        }
+    }
+}
+
+__host__ __device__ __forceinline__ int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace ccb

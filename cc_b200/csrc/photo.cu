@@ -1,0 +1,579 @@
+// photo.cu - fused multi-scale photometric loss (warp + valid/occlusion masks + 13x13 SSIM +
+// robust L1 + reductions) forward and hand-derived backward, plus the consensus-target variant.
+//
+// One launch covers every pyramid level: block -> (level, batch, 64x20 tile) through a prefix table.
+// Each CTA stages the target tile (+6 px halo) in shared memory once, then loops over the reference
+// frames: warp the reference into a second shared tile (projection + bilinear gather, or flow
+// coordinates), run the separable 13-tap Gaussian moments out of shared memory
+// (rows -> smem, columns -> registers), and finish SSIM / robust-L1 / mask terms in registers.
+//
+// Roofline note: with the reference's real 13x13 window the kernel is FP32-FMA bound
+// (~1.4 kFMA per level-pixel forward), not HBM bound; with wssim == 0 the SSIM stage is compiled
+// out (template SSIM=false) and the kernel is a pure streaming pass.
+//
+// Reference: loss_functions.py:27-128,132-137,160-202,343-352; inverse_warp.py:164-283; ssim.py:9-36.
+#include "ssim_tile.cuh"
+
+namespace ccb {
+
+struct PhotoArgs {
+    ccb_photo_desc d;
+    int blk_off[CCB_MAX_LEVELS + 1];
+    float omw;               // (1 - wssim) evaluated in double on the host, like the reference
+};
+
+__device__ __forceinline__ void locate_block(const PhotoArgs& a, int& l, int& b, int& x0, int& y0, int& local) {
+    int blk = blockIdx.x;
+    l = 0;
+    while (l + 1 < a.d.nlevels && blk >= a.blk_off[l + 1]) ++l;
+    local = blk - a.blk_off[l];
+    const int w = a.d.w[l], h = a.d.h[l];
+    const int tx_n = cdiv(w, TW), ty_n = cdiv(h, TH);
+    b = local / (tx_n * ty_n);
+    int t = local - b * tx_n * ty_n;
+    y0 = (t / tx_n) * TH;
+    x0 = (t % tx_n) * TW;
+}
+
+// ================================================================================================
+// Forward.  MODE: CCB_PHOTO_RIGID / FLOW / CONSENSUS.  SSIM=false compiles the 13x13 stage out.
+template <int MODE, bool SSIM>
+__global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
+    constexpr int HALO = SSIM ? 6 : 0;
+    using T = Tile<HALO>;
+    CCB_DYN_SMEM(smem_raw);
+    float* sx = reinterpret_cast<float*>(smem_raw);   // [3][PLANE] target
+    float* sy = sx + 3 * T::PLANE;                    // [3][PLANE] warped reference
+    float* sH = sy + 3 * T::PLANE;                    // [3][RH*HP]  (SSIM only)
+    __shared__ Cam s_cam[3];                          // 0: scaled cam of ref i; 1,2: unscaled (bw, fw) for occ
+    __shared__ float s_red[4 * 32];
+    __shared__ float s_g[CCB_SSIM_TAPS];
+
+    const ccb_photo_desc& d = a.d;
+    int l, b, x0, y0, local;
+    locate_block(a, l, b, x0, y0, local);
+    const int h = d.h[l], w = d.w[l], R = d.R;
+    const long long hw = (long long)h * w;
+    const int tid = threadIdx.x;
+    const int col = tid & 63, rg = tid >> 6;
+    const float w1 = (float)(w - 1), h1 = (float)(h - 1);
+    if (tid < CCB_SSIM_TAPS) s_g[tid] = d.taps[tid];
+
+    // ---- stage the target tile (+halo); zero outside the image == conv zero padding
+    const float* tgt = d.tgt[l] + (long long)b * 3 * hw;
+    for (int idx = tid; idx < T::RH * T::RW; idx += NT) {
+        int ry = idx / T::RW, rx = idx - ry * T::RW;
+        int gy = y0 - HALO + ry, gx = x0 - HALO + rx;
+        bool in = (gy >= 0) && (gy < h) && (gx >= 0) && (gx < w);
+        long long off = (long long)gy * w + gx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sx[c * T::PLANE + ry * T::PITCH + rx] = in ? __ldg(tgt + c * hw + off) : 0.f;
+    }
+    __syncthreads();
+
+    // ---- target moments, shared by all reference frames
+    float mu1[3][PXT], exx[3][PXT];
+    if (SSIM) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            hpass<0>(sx + c * Tile<6>::PLANE, nullptr, nullptr, sH, s_g);
+            __syncthreads();
+            float o[2][PXT];
+            vpass<2>(sH, s_g, o);
+#pragma unroll
+            for (int j = 0; j < PXT; ++j) { mu1[c][j] = o[0][j]; exx[c][j] = o[1][j]; }
+            __syncthreads();
+        }
+    }
+
+    // consensus accumulators: first rigid error / validity, then the combined rigid error
+    float cons_e0[PXT], cons_v0[PXT], cons_cam[PXT];
+
+    for (int i = 0; i < R; ++i) {
+        // ---- per-ref cameras
+        if (MODE == CCB_PHOTO_RIGID) {
+            if (tid == 0) {
+                const float* Kb = d.K + b * 9;
+                const float* Kib = d.Kinv + b * 9;
+                make_cam(d.pose + ((long long)b * R + i) * 6, Kb, Kib, (float)d.H / (float)h, d.rotation_mode, w, h, s_cam[0]);
+                if (d.has_occ) {
+                    int lo = (i < R - 1 - i) ? i : R - 1 - i, hi = R - 1 - lo;
+                    make_cam(d.pose + ((long long)b * R + lo) * 6, Kb, Kib, 1.f, d.rotation_mode, w, h, s_cam[1]);
+                    make_cam(d.pose + ((long long)b * R + hi) * 6, Kb, Kib, 1.f, d.rotation_mode, w, h, s_cam[2]);
+                }
+            }
+            __syncthreads();
+        }
+        // ---- warp the reference into sy over the staged region
+        const float* ref = d.ref[l][i] + (long long)b * 3 * hw;
+        for (int idx = tid; idx < T::RH * T::RW; idx += NT) {
+            int ry = idx / T::RW, rx = idx - ry * T::RW;
+            int gy = y0 - HALO + ry, gx = x0 - HALO + rx;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+            if ((gy >= 0) && (gy < h) && (gx >= 0) && (gx < w)) {
+                float Xn, Yn;
+                int pad = CCB_PAD_ZEROS;
+                if (MODE == CCB_PHOTO_RIGID) {
+                    float dep = __ldg(d.depth[l] + (long long)b * hw + (long long)gy * w + gx);
+                    Proj p = project(s_cam[0], (float)gx, (float)gy, dep, d.padding_mode == CCB_PAD_ZEROS);
+                    Xn = p.Xn; Yn = p.Yn;
+                    pad = d.padding_mode;
+                } else {
+                    const float* fl = d.flow[l][i] + (long long)b * 2 * hw + (long long)gy * w + gx;
+                    flow_coords((float)gx, (float)gy, __ldg(fl), __ldg(fl + hw), w1, h1, Xn, Yn);
+                }
+                Samp s = make_samp(Xn, Yn, w, h, pad);
+                v0 = interp(fetch(ref, s, w), s);
+                v1 = interp(fetch(ref + hw, s, w), s);
+                v2 = interp(fetch(ref + 2 * hw, s, w), s);
+            }
+            int o = ry * T::PITCH + rx;
+            sy[o] = v0; sy[T::PLANE + o] = v1; sy[2 * T::PLANE + o] = v2;
+        }
+        __syncthreads();
+
+        // ---- centre-pixel scalars (valid, occlusion, mask)
+        float valid[PXT], om[PXT], mk[PXT];   // om = (1-occ)
+        bool inimg[PXT];
+#pragma unroll
+        for (int j = 0; j < PXT; ++j) {
+            int py = y0 + rg * PXT + j, px = x0 + col;
+            inimg[j] = (py < h) && (px < w);
+            int o = (rg * PXT + j + HALO) * T::PITCH + col + HALO;
+            float wv0 = sy[o], wv1 = sy[T::PLANE + o], wv2 = sy[2 * T::PLANE + o];
+            valid[j] = ((wv0 != 0.f) || (wv1 != 0.f) || (wv2 != 0.f)) ? 1.f : 0.f;
+            om[j] = 1.f; mk[j] = 1.f;
+            if (inimg[j] && MODE != CCB_PHOTO_CONSENSUS) {
+                long long off = (long long)py * w + px;
+                if (d.has_occ) {
+                    float occ;
+                    if (MODE == CCB_PHOTO_RIGID) {
+                        float dep = __ldg(d.depth[l] + (long long)b * hw + off);
+                        Proj pb = project(s_cam[1], (float)px, (float)py, dep, false);
+                        Proj pf = project(s_cam[2], (float)px, (float)py, dep, false);
+                        float ub, vb, uf, vf;
+                        coords_to_flow(s_cam[1], pb.Xn, pb.Yn, (float)px, (float)py, ub, vb);
+                        coords_to_flow(s_cam[2], pf.Xn, pf.Yn, (float)px, (float)py, uf, vf);
+                        occ = occ_mask(ub, vb, uf, vf);
+                    } else {
+                        const float* fb = d.flow[l][0] + (long long)b * 2 * hw + off;
+                        const float* ff = d.flow[l][1] + (long long)b * 2 * hw + off;
+                        occ = occ_mask(__ldg(fb), __ldg(fb + hw), __ldg(ff), __ldg(ff + hw));
+                    }
+                    om[j] = 1.f - occ;
+                }
+                if (d.has_mask) mk[j] = __ldg(d.mask[l] + ((long long)b * R + i) * hw + off);
+            }
+        }
+
+        // ---- per-channel SSIM + loss terms
+        float s_l1 = 0.f, s_ss = 0.f, s_va = 0.f, s_ob = 0.f;
+        float gm[PXT], e_l1[PXT], e_ss[PXT];
+#pragma unroll
+        for (int j = 0; j < PXT; ++j) { gm[j] = 0.f; e_l1[j] = 0.f; e_ss[j] = 0.f; }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float o3[3][PXT];
+            if (SSIM) {
+                hpass<1>(sx + c * Tile<6>::PLANE, sy + c * Tile<6>::PLANE, nullptr, sH, s_g);
+                __syncthreads();
+                vpass<3>(sH, s_g, o3);
+            }
+#pragma unroll
+            for (int j = 0; j < PXT; ++j) {
+                int o = c * T::PLANE + (rg * PXT + j + HALO) * T::PITCH + col + HALO;
+                float tv = sx[o], wv = sy[o];
+                float S = 0.f, dmu2 = 0.f, deyy = 0.f, dexy = 0.f;
+                if (SSIM) S = ssim_point(mu1[c][j], exx[c][j], o3[0][j], o3[1][j], o3[2][j], dmu2, deyy, dexy);
+                if (MODE == CCB_PHOTO_CONSENSUS) {
+                    e_l1[j] += rl1(tv - wv, 0.5f);
+                    e_ss[j] += (1.f - S);
+                } else if (inimg[j]) {
+                    float e = (tv - wv) * valid[j] * om[j];      // (1-occ) in {0,1}: order-free
+                    float df = e * mk[j];
+                    s_l1 += rl1(df, d.qch);
+                    float sl = (1.f - S * valid[j]) * om[j];
+                    s_ss += sl * mk[j];
+                    if (d.has_mask) gm[j] += rl1_d(df, d.qch) * e + d.wssim * sl;
+                    if (SSIM) {
+                        float gam = -valid[j] * om[j] * mk[j];
+                        long long off = (long long)(y0 + rg * PXT + j) * w + (x0 + col);
+                        float* dm = d.dmaps[l] + (((long long)b * R + i) * 9 + c * 3) * hw + off;
+                        dm[0] = gam * dmu2;
+                        dm[hw] = gam * deyy;
+                        dm[2 * hw] = gam * dexy;
+                    }
+                }
+            }
+            if (SSIM) __syncthreads();   // sH is rewritten by the next channel / ref
+        }
+
+        if (MODE == CCB_PHOTO_CONSENSUS) {
+#pragma unroll
+            for (int j = 0; j < PXT; ++j) {
+                // loss_functions.py:184-198: min over (fwd,bwd) rigid errors vs the flow error
+                float e = a.omw * (e_l1[j] / 3.f) + d.wssim * (e_ss[j] / 3.f);
+                if (i == 0) { cons_e0[j] = e; cons_v0[j] = valid[j]; }
+                else if (i == 1) {
+                    float vcam = 1.f - (1.f - cons_v0[j]) * (1.f - valid[j]);
+                    cons_cam[j] = fminf(cons_e0[j], e) * vcam;
+                } else {
+                    int py = y0 + rg * PXT + j, px = x0 + col;
+                    if ((py < h) && (px < w))
+                        d.target[l][(long long)b * hw + (long long)py * w + px] =
+                            (d.wrig * cons_cam[j] <= (e + 1e-8f)) ? 1.f : 0.f;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < PXT; ++j) {
+                if (!inimg[j]) continue;
+                long long off = ((long long)b * R + i) * hw + (long long)(y0 + rg * PXT + j) * w + (x0 + col);
+                s_va += valid[j];
+                s_ob += rl1(1.f - valid[j], d.qch);
+                d.vo[l][off] = valid[j] * om[j];
+                if (d.has_mask) d.gmask[l][off] = gm[j];
+            }
+            float red[4] = {s_l1, s_ss, s_va, s_ob};
+            block_sum<4>(red, s_red);
+            if (tid == 0) {
+                float* po = d.partials + ((long long)blockIdx.x * R + i) * 4;
+                po[0] = red[0]; po[1] = red[1]; po[2] = red[2]; po[3] = red[3];
+            }
+        }
+        __syncthreads();   // sy / s_cam reuse
+    }
+
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward finalize: per (level, ref) sums -> oob normalisation, loss terms, total loss.
+// loss_functions.py:48,58-59 / 103,114
+__global__ void photo_fwd_finalize(const PhotoArgs a) {
+    __shared__ float s_red[4 * 32];
+    __shared__ float s_total;
+    const ccb_photo_desc& d = a.d;
+    if (threadIdx.x == 0) s_total = 0.f;
+    __syncthreads();
+    for (int l = 0; l < d.nlevels; ++l) {
+        const int nblk = a.blk_off[l + 1] - a.blk_off[l];
+        for (int i = 0; i < d.R; ++i) {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = threadIdx.x; k < nblk; k += blockDim.x) {
+                const float* p = d.partials + ((long long)(a.blk_off[l] + k) * d.R + i) * 4;
+                v[0] += p[0]; v[1] += p[1]; v[2] += p[2]; v[3] += p[3];
+            }
+            block_sum<4>(v, s_red);
+            if (threadIdx.x == 0) {
+                float npx = (float)((long long)d.B * d.h[l] * d.w[l]);
+                float n = 3.f * npx;
+                float oob = npx / v[2];
+                float L = a.omw * oob * (v[0] / n + d.wssim * (v[1] / n)) + d.lambda_oob * (v[3] / npx);
+                float* sc = d.scal + ((long long)l * d.R + i) * 4;
+                sc[0] = a.omw * oob / n;
+                sc[1] = oob;
+                sc[2] = v[2];
+                sc[3] = L;
+                s_total += L;
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) d.loss[0] = s_total;
+}
+
+// ================================================================================================
+// Backward.  Blurs the saved gamma*dS maps (halo 6), recomputes the centre-pixel warp, and chains to
+// depth / pose (rigid) or flow; mask gradient is a scale of the saved unscaled term.
+template <int MODE, bool SSIM>
+__global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(const PhotoArgs a) {
+    using T = Tile<6>;
+    CCB_DYN_SMEM(smem_raw);
+    float* sD = reinterpret_cast<float*>(smem_raw);   // [3][PLANE] dS maps of one channel
+    float* sH = sD + 3 * T::PLANE;                    // [3][RH*HP]
+    __shared__ Cam s_cam;
+    __shared__ float s_red[12 * 32];
+    __shared__ float s_g[CCB_SSIM_TAPS];
+
+    const ccb_photo_desc& d = a.d;
+    int l, b, x0, y0, local;
+    locate_block(a, l, b, x0, y0, local);
+    const int h = d.h[l], w = d.w[l], R = d.R;
+    const long long hw = (long long)h * w;
+    const int tid = threadIdx.x;
+    const int col = tid & 63, rg = tid >> 6;
+    const float w1 = (float)(w - 1), h1 = (float)(h - 1);
+    if (tid < CCB_SSIM_TAPS) s_g[tid] = d.taps[tid];
+    const float go = __ldg(d.grad_out);
+    const float* tgt = d.tgt[l] + (long long)b * 3 * hw;
+
+    float gd[PXT];
+#pragma unroll
+    for (int j = 0; j < PXT; ++j) gd[j] = 0.f;
+    __syncthreads();
+
+    for (int i = 0; i < R; ++i) {
+        const float c_l = go * __ldg(d.scal + ((long long)l * R + i) * 4);
+        const float c_s = c_l * d.wssim;
+        if (MODE == CCB_PHOTO_RIGID) {
+            if (tid == 0)
+                make_cam(d.pose + ((long long)b * R + i) * 6, d.K + b * 9, d.Kinv + b * 9, (float)d.H / (float)h,
+                         d.rotation_mode, w, h, s_cam);
+        }
+        // ---- blur the three dS maps of every channel
+        float bl[3][3][PXT];
+        if (SSIM) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* dm = d.dmaps[l] + (((long long)b * R + i) * 9 + c * 3) * hw;
+                for (int idx = tid; idx < T::RH * T::RW; idx += NT) {
+                    int ry = idx / T::RW, rx = idx - ry * T::RW;
+                    int gy = y0 - 6 + ry, gx = x0 - 6 + rx;
+                    bool in = (gy >= 0) && (gy < h) && (gx >= 0) && (gx < w);
+                    long long off = (long long)gy * w + gx;
+                    int o = ry * T::PITCH + rx;
+                    sD[o] = in ? __ldg(dm + off) : 0.f;
+                    sD[T::PLANE + o] = in ? __ldg(dm + hw + off) : 0.f;
+                    sD[2 * T::PLANE + o] = in ? __ldg(dm + 2 * hw + off) : 0.f;
+                }
+                __syncthreads();
+                hpass<2>(sD, sD + T::PLANE, sD + 2 * T::PLANE, sH, s_g);
+                __syncthreads();
+                vpass<3>(sH, s_g, bl[c]);
+            }
+        }
+        __syncthreads();   // s_cam visible; sD/sH free
+
+        const float* ref = d.ref[l][i] + (long long)b * 3 * hw;
+        float acc[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < PXT; ++j) {
+            int py = y0 + rg * PXT + j, px = x0 + col;
+            if ((py < h) && (px < w)) {
+                long long off = (long long)py * w + px;
+                long long moff = ((long long)b * R + i) * hw + off;
+                float Xn, Yn;
+                Proj p;
+                int pad = CCB_PAD_ZEROS;
+                if (MODE == CCB_PHOTO_RIGID) {
+                    float dep = __ldg(d.depth[l] + (long long)b * hw + off);
+                    p = project(s_cam, (float)px, (float)py, dep, d.padding_mode == CCB_PAD_ZEROS);
+                    Xn = p.Xn; Yn = p.Yn;
+                    pad = d.padding_mode;
+                } else {
+                    const float* fl = d.flow[l][i] + (long long)b * 2 * hw + off;
+                    flow_coords((float)px, (float)py, __ldg(fl), __ldg(fl + hw), w1, h1, Xn, Yn);
+                }
+                Samp s = make_samp(Xn, Yn, w, h, pad);
+                float vo = __ldg(d.vo[l] + moff);
+                float mk = d.has_mask ? __ldg(d.mask[l] + moff) : 1.f;
+                float M = vo * mk;
+                float gix = 0.f, giy = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    Corners cr = fetch(ref + c * hw, s, w);
+                    float wv = interp(cr, s);
+                    float tv = __ldg(tgt + c * hw + off);
+                    float df = (tv - wv) * M;
+                    float gw = -c_l * rl1_d(df, d.qch) * M;
+                    if (SSIM) gw += c_s * (bl[c][0][j] + 2.f * wv * bl[c][1][j] + tv * bl[c][2][j]);
+                    gix += gw * interp_dx(cr, s);
+                    giy += gw * interp_dy(cr, s);
+                }
+                float gXn = gix * s.gmx, gYn = giy * s.gmy;
+                if (MODE == CCB_PHOTO_RIGID) {
+                    gd[j] += project_bwd(s_cam, p, gXn, gYn, acc);
+                } else {
+                    float* df = d.d_flow[l][i] + (long long)b * 2 * hw + off;
+                    df[0] = gXn * (2.f / w1);
+                    df[hw] = gYn * (2.f / h1);
+                }
+                if (d.has_mask) d.d_mask[l][moff] = c_l * __ldg(d.gmask[l] + moff);
+            }
+        }
+        if (MODE == CCB_PHOTO_RIGID) {
+            block_sum<12>(acc, s_red);
+            if (tid == 0) {
+                float* po = d.pose_partials + ((long long)blockIdx.x * R + i) * 12;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) po[k] = acc[k];
+            }
+        }
+        __syncthreads();
+    }
+    if (MODE == CCB_PHOTO_RIGID) {
+#pragma unroll
+        for (int j = 0; j < PXT; ++j) {
+            int py = y0 + rg * PXT + j, px = x0 + col;
+            if ((py < h) && (px < w)) d.d_depth[l][(long long)b * hw + (long long)py * w + px] = gd[j];
+        }
+    }
+}
+
+// One warp per (b, ref): sum the per-tile dP partials of every level, chain to the 6-DoF pose.
+__global__ void photo_pose_finalize(const PhotoArgs a) {
+    const ccb_photo_desc& d = a.d;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= d.B * d.R) return;
+    const int b = wid / d.R, i = wid - b * d.R;
+    float dpose[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int l = 0; l < d.nlevels; ++l) {
+        const int per_b = (a.blk_off[l + 1] - a.blk_off[l]) / d.B;
+        float dP[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) dP[k] = 0.f;
+        for (int t = lane; t < per_b; t += 32) {
+            const float* p = d.pose_partials + ((long long)(a.blk_off[l] + b * per_b + t) * d.R + i) * 12;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) dP[k] += p[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) dP[k] = warp_sum(dP[k]);
+        if (lane == 0) {
+            Cam cm;
+            make_cam(d.pose + ((long long)b * d.R + i) * 6, d.K + b * 9, d.Kinv + b * 9,
+                     (float)d.H / (float)d.h[l], d.rotation_mode, d.w[l], d.h[l], cm);
+            pose_grad_from_dP(cm, dP, d.rotation_mode, dpose);
+        }
+    }
+    if (lane == 0) {
+        float* o = d.d_pose + ((long long)b * d.R + i) * 6;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o[k] = dpose[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+static int fill_args(const ccb_photo_desc* d, PhotoArgs& a) {
+    CCB_REQUIRE(d != nullptr, CCB_ERR_ARG, "photo: null descriptor");
+    CCB_REQUIRE(d->nlevels >= 1 && d->nlevels <= CCB_MAX_LEVELS, CCB_ERR_ARG, "photo: nlevels %d out of range", d->nlevels);
+    CCB_REQUIRE(d->B >= 1 && d->R >= 1 && d->R <= CCB_MAX_REFS, CCB_ERR_ARG, "photo: bad B=%d R=%d", d->B, d->R);
+    a.d = *d;
+    a.omw = d->one_minus_wssim;
+    a.blk_off[0] = 0;
+    for (int l = 0; l < d->nlevels; ++l) {
+        CCB_REQUIRE(d->h[l] >= 2 && d->w[l] >= 2, CCB_ERR_ARG, "photo: level %d size %dx%d too small", l, d->h[l], d->w[l]);
+        a.blk_off[l + 1] = a.blk_off[l] + d->B * cdiv(d->w[l], TW) * cdiv(d->h[l], TH);
+    }
+    for (int l = d->nlevels + 1; l <= CCB_MAX_LEVELS; ++l) a.blk_off[l] = a.blk_off[d->nlevels];
+    return CCB_OK;
+}
+
+template <int HALO>
+static size_t fwd_smem() { return (size_t)(6 * Tile<HALO>::PLANE + (HALO ? 3 * Tile<HALO>::RH * HP : 0)) * sizeof(float); }
+static size_t bwd_smem() { return (size_t)(3 * Tile<6>::PLANE + 3 * Tile<6>::RH * HP) * sizeof(float); }
+
+template <int MODE, bool SSIM>
+static int launch_fwd(const PhotoArgs& a, cudaStream_t st) {
+    auto k = photo_fwd_kernel<MODE, SSIM>;
+    size_t sm = SSIM ? fwd_smem<6>() : fwd_smem<0>();
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    CCB_LAUNCH(k, dim3(a.blk_off[a.d.nlevels]), dim3(NT), sm, st, a);
+    return check_launch("photo_fwd");
+}
+template <int MODE, bool SSIM>
+static int launch_bwd(const PhotoArgs& a, cudaStream_t st) {
+    auto k = photo_bwd_kernel<MODE, SSIM>;
+    size_t sm = bwd_smem();
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    CCB_LAUNCH(k, dim3(a.blk_off[a.d.nlevels]), dim3(NT), sm, st, a);
+    return check_launch("photo_bwd");
+}
+
+}  // namespace ccb
+
+using namespace ccb;
+
+extern "C" long long ccb_photo_partials_floats(const ccb_photo_desc* d) {
+    PhotoArgs a;
+    if (fill_args(d, a) != CCB_OK) return -1;
+    return (long long)a.blk_off[d->nlevels] * d->R * 4;
+}
+extern "C" long long ccb_photo_pose_partials_floats(const ccb_photo_desc* d) {
+    PhotoArgs a;
+    if (fill_args(d, a) != CCB_OK) return -1;
+    return (long long)a.blk_off[d->nlevels] * d->R * 12;
+}
+
+static int check_common(const ccb_photo_desc* d, bool bwd) {
+    for (int l = 0; l < d->nlevels; ++l) {
+        CCB_REQUIRE(d->tgt[l] != nullptr, CCB_ERR_ARG, "photo: tgt[%d] is null", l);
+        for (int i = 0; i < d->R; ++i) {
+            CCB_REQUIRE(d->ref[l][i] != nullptr, CCB_ERR_ARG, "photo: ref[%d][%d] is null", l, i);
+            if (d->mode != CCB_PHOTO_RIGID) CCB_REQUIRE(d->flow[l][i] != nullptr, CCB_ERR_ARG, "photo: flow[%d][%d] is null", l, i);
+        }
+        if (d->mode == CCB_PHOTO_RIGID) CCB_REQUIRE(d->depth[l] != nullptr, CCB_ERR_ARG, "photo: depth[%d] is null", l);
+        if (d->has_mask) CCB_REQUIRE(d->mask[l] != nullptr, CCB_ERR_ARG, "photo: mask[%d] is null", l);
+        if (d->mode != CCB_PHOTO_CONSENSUS) {
+            CCB_REQUIRE(d->vo[l] != nullptr, CCB_ERR_ARG, "photo: vo[%d] is null", l);
+            if (d->wssim != 0.f) CCB_REQUIRE(d->dmaps[l] != nullptr, CCB_ERR_ARG, "photo: dmaps[%d] is null", l);
+            if (d->has_mask) CCB_REQUIRE(d->gmask[l] != nullptr, CCB_ERR_ARG, "photo: gmask[%d] is null", l);
+        }
+    }
+    if (d->mode == CCB_PHOTO_RIGID) {
+        CCB_REQUIRE(d->pose && d->K && d->Kinv, CCB_ERR_ARG, "photo: pose/K/Kinv null");
+        CCB_REQUIRE(!d->has_occ || d->R == 4, CCB_ERR_ARG,
+                    "photo: rigid occlusion masks need 4 reference frames (loss_functions.py:133-135), got %d", d->R);
+        CCB_REQUIRE(d->padding_mode == CCB_PAD_ZEROS || d->padding_mode == CCB_PAD_BORDER, CCB_ERR_ARG, "photo: bad padding_mode");
+    }
+    if (d->mode == CCB_PHOTO_FLOW) CCB_REQUIRE(!d->has_occ || d->R == 2, CCB_ERR_ARG, "photo: flow occlusion needs R == 2");
+    (void)bwd;
+    return CCB_OK;
+}
+
+extern "C" int ccb_photo_loss_fwd(const ccb_photo_desc* d, ccb_stream_t stream) {
+    PhotoArgs a;
+    int rc = fill_args(d, a);
+    if (rc) return rc;
+    CCB_REQUIRE(d->mode == CCB_PHOTO_RIGID || d->mode == CCB_PHOTO_FLOW, CCB_ERR_ARG, "photo_loss_fwd: bad mode %d", d->mode);
+    rc = check_common(d, false);
+    if (rc) return rc;
+    CCB_REQUIRE(d->partials && d->scal && d->loss, CCB_ERR_ARG, "photo_loss_fwd: partials/scal/loss null");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool ss = d->wssim != 0.f;
+    if (d->mode == CCB_PHOTO_RIGID) rc = ss ? launch_fwd<CCB_PHOTO_RIGID, true>(a, st) : launch_fwd<CCB_PHOTO_RIGID, false>(a, st);
+    else rc = ss ? launch_fwd<CCB_PHOTO_FLOW, true>(a, st) : launch_fwd<CCB_PHOTO_FLOW, false>(a, st);
+    if (rc) return rc;
+    CCB_LAUNCH(photo_fwd_finalize, dim3(1), dim3(128), 0, st, a);
+    return check_launch("photo_fwd_finalize");
+}
+
+extern "C" int ccb_photo_loss_bwd(const ccb_photo_desc* d, ccb_stream_t stream) {
+    PhotoArgs a;
+    int rc = fill_args(d, a);
+    if (rc) return rc;
+    CCB_REQUIRE(d->mode == CCB_PHOTO_RIGID || d->mode == CCB_PHOTO_FLOW, CCB_ERR_ARG, "photo_loss_bwd: bad mode %d", d->mode);
+    rc = check_common(d, true);
+    if (rc) return rc;
+    CCB_REQUIRE(d->grad_out && d->scal, CCB_ERR_ARG, "photo_loss_bwd: grad_out/scal null");
+    for (int l = 0; l < d->nlevels; ++l) {
+        if (d->mode == CCB_PHOTO_RIGID) CCB_REQUIRE(d->d_depth[l] != nullptr, CCB_ERR_ARG, "photo_loss_bwd: d_depth[%d] null", l);
+        else for (int i = 0; i < d->R; ++i) CCB_REQUIRE(d->d_flow[l][i] != nullptr, CCB_ERR_ARG, "photo_loss_bwd: d_flow[%d][%d] null", l, i);
+        if (d->has_mask) CCB_REQUIRE(d->d_mask[l] != nullptr, CCB_ERR_ARG, "photo_loss_bwd: d_mask[%d] null", l);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool ss = d->wssim != 0.f;
+    if (d->mode == CCB_PHOTO_RIGID) {
+        CCB_REQUIRE(d->d_pose && d->pose_partials, CCB_ERR_ARG, "photo_loss_bwd: d_pose/pose_partials null");
+        rc = ss ? launch_bwd<CCB_PHOTO_RIGID, true>(a, st) : launch_bwd<CCB_PHOTO_RIGID, false>(a, st);
+        if (rc) return rc;
+        int nw = d->B * d->R;
+        CCB_LAUNCH(photo_pose_finalize, dim3(cdiv(nw * 32, 128)), dim3(128), 0, st, a);
+        return check_launch("photo_pose_finalize");
+    }
+    return ss ? launch_bwd<CCB_PHOTO_FLOW, true>(a, st) : launch_bwd<CCB_PHOTO_FLOW, false>(a, st);
+}
+
+extern "C" int ccb_consensus_targets(const ccb_photo_desc* d, ccb_stream_t stream) {
+    PhotoArgs a;
+    int rc = fill_args(d, a);
+    if (rc) return rc;
+    CCB_REQUIRE(d->mode == CCB_PHOTO_CONSENSUS && d->R == 3, CCB_ERR_ARG, "consensus_targets: mode must be CONSENSUS with R == 3");
+    rc = check_common(d, false);
+    if (rc) return rc;
+    for (int l = 0; l < d->nlevels; ++l) CCB_REQUIRE(d->target[l] != nullptr, CCB_ERR_ARG, "consensus_targets: target[%d] null", l);
+    cudaStream_t st = (cudaStream_t)stream;
+    return (d->wssim != 0.f) ? launch_fwd<CCB_PHOTO_CONSENSUS, true>(a, st) : launch_fwd<CCB_PHOTO_CONSENSUS, false>(a, st);
+}

@@ -1,0 +1,196 @@
+/* ccb200.h - C ABI of libccb200.so: the B200 (sm_100a) implementation of the Competitive-Collaboration
+ * training step's dense per-pixel path (anuragranj/cc @ 2b4e362).
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer to contiguous fp32 NCHW data unless a comment says "host";
+ *   - the caller (torch.empty on the Python side) owns every buffer, including workspaces and the
+ *     buffers saved for backward; the library owns no tensors and keeps no global mutable state
+ *     (the reference caches a module-global pixel grid, inverse_warp.py:10 - we do not);
+ *   - every entry point is asynchronous on `stream` (a cudaStream_t), never synchronises the host,
+ *     never throws, and returns CCB_OK or a negative ccb_status; ccb_last_error_string() explains it;
+ *   - shape errors that the reference reports as Python AssertionError (inverse_warp.py:23-28) are
+ *     raised by the Python mirror (cc_b200/*.py) before the call; the ABI re-checks what it needs.
+ *
+ * Each entry point names the reference interface it replaces (file:line relative to the reference).
+ */
+#ifndef CCB200_H
+#define CCB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCB_MAX_LEVELS 8
+#define CCB_MAX_REFS 4
+#define CCB_SSIM_TAPS 13
+
+typedef void* ccb_stream_t; /* cudaStream_t */
+
+typedef enum ccb_status {
+    CCB_OK = 0,
+    CCB_ERR_ARG = -1,         /* bad size / null pointer / unsupported combination */
+    CCB_ERR_LAUNCH = -2,      /* CUDA launch or runtime error */
+    CCB_ERR_UNSUPPORTED = -3
+} ccb_status;
+
+const char* ccb_last_error_string(void);
+int ccb_version(void);
+/* 1 only for the CPU execution-model simulator build used by the GPU-less unit tests (tests/sim). */
+int ccb_is_simulator(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Image pyramid: level l = exact 2^l x 2^l box mean of the full-resolution planes.
+ * Replaces the 15 adaptive_avg_pool2d calls per level per step (loss_functions.py:36-37,89-90,
+ * 163-165,315).  out_levels: HOST array of nlevels-1 device pointers (levels 1..nlevels-1),
+ * each [planes, H>>l, W>>l].  H and W must be divisible by 2^(nlevels-1).
+ * ---------------------------------------------------------------------------------------------- */
+int ccb_image_pyramid(const float* img, int planes, int H, int W, int nlevels,
+                      float* const* out_levels, ccb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-scale photometric loss (one launch covers every pyramid level).
+ *   mode CCB_PHOTO_RIGID : photometric_reconstruction_loss  (loss_functions.py:80-128)
+ *        = pixel2cam -> pose_vec2mat -> cam2pixel -> bilinear sample (inverse_warp.py:250-283)
+ *          + depth_occlusion_masks (loss_functions.py:132-137,343-352) + SSIM 13x13 (ssim.py:19-36)
+ *          + robust L1 (loss_functions.py:18-21) + oob normalisation.
+ *   mode CCB_PHOTO_FLOW  : photometric_flow_loss             (loss_functions.py:27-77)
+ *        = flow_warp (inverse_warp.py:164-192) + occlusion_masks + SSIM + robust L1.
+ *   mode CCB_PHOTO_CONSENSUS : consensus_exp_masks targets   (loss_functions.py:160-202), R = 3
+ *        "refs": (ref_fwd,cam_flow_fwd) (ref_bwd,cam_flow_bwd) (ref_fwd,flow_fwd); no gradient.
+ * ---------------------------------------------------------------------------------------------- */
+enum { CCB_PHOTO_RIGID = 0, CCB_PHOTO_FLOW = 1, CCB_PHOTO_CONSENSUS = 2 };
+enum { CCB_ROT_EULER = 0, CCB_ROT_QUAT = 1 };
+enum { CCB_PAD_ZEROS = 0, CCB_PAD_BORDER = 1, CCB_PAD_NONE = 2 };
+
+typedef struct ccb_photo_desc {
+    int mode;
+    int B, R;                 /* batch, number of reference frames (<= CCB_MAX_REFS) */
+    int H, W;                 /* full-resolution size: downscale_l = H / h[l] (loss_functions.py:87) */
+    int nlevels;
+    int h[CCB_MAX_LEVELS], w[CCB_MAX_LEVELS];
+    int has_mask;             /* explainability mask given (mask[l] != NULL for all l) */
+    int has_occ;              /* apply occlusion masks (always 1 in the reference paths) */
+    int rotation_mode;        /* CCB_ROT_* (rigid) */
+    int padding_mode;         /* CCB_PAD_ZEROS | CCB_PAD_BORDER (rigid) */
+    float wssim, qch, lambda_oob, wrig;
+    float one_minus_wssim;    /* (1 - wssim) evaluated in double by the caller, as the reference does */
+    float taps[CCB_SSIM_TAPS]; /* fp32 Gaussian taps exactly as ssim.py:9-11 builds them */
+    /* inputs */
+    const float* tgt[CCB_MAX_LEVELS];                 /* [B,3,h,w] pooled target frame */
+    const float* ref[CCB_MAX_LEVELS][CCB_MAX_REFS];   /* [B,3,h,w] pooled reference frames */
+    const float* depth[CCB_MAX_LEVELS];               /* rigid: [B,1,h,w] */
+    const float* flow[CCB_MAX_LEVELS][CCB_MAX_REFS];  /* flow/consensus: [B,2,h,w] */
+    const float* mask[CCB_MAX_LEVELS];                /* [B,R,h,w] or NULL */
+    const float* pose;                                /* rigid: [B,R,6] */
+    const float* K;                                   /* rigid: [B,3,3] full-res intrinsics */
+    const float* Kinv;                                /* rigid: [B,3,3] */
+    /* saved for backward (written by fwd, read by bwd) */
+    float* dmaps[CCB_MAX_LEVELS];    /* [B,R,9,h,w] gamma * dS/d(mu2,Eyy,Exy); unused when wssim == 0 */
+    float* gmask[CCB_MAX_LEVELS];    /* [B,R,h,w]  unscaled d loss / d mask (has_mask only) */
+    float* vo[CCB_MAX_LEVELS];       /* [B,R,h,w]  valid * (1 - occ) */
+    float* scal;                     /* [nlevels,R,4] : c_l, oob, sum_valid, level-ref loss */
+    /* forward outputs / workspace */
+    float* partials;                 /* [ccb_photo_partials_floats()] */
+    float* loss;                     /* [1] */
+    float* target[CCB_MAX_LEVELS];   /* consensus: [B,1,h,w] 0/1 */
+    /* backward inputs / outputs / workspace */
+    const float* grad_out;           /* [1] d L / d loss */
+    float* d_depth[CCB_MAX_LEVELS];                 /* rigid: [B,1,h,w] */
+    float* d_flow[CCB_MAX_LEVELS][CCB_MAX_REFS];    /* flow:  [B,2,h,w] */
+    float* d_mask[CCB_MAX_LEVELS];                  /* [B,R,h,w] (has_mask) */
+    float* d_pose;                                  /* rigid: [B,R,6] */
+    float* pose_partials;            /* [ccb_photo_pose_partials_floats()] */
+} ccb_photo_desc;
+
+long long ccb_photo_partials_floats(const ccb_photo_desc* d);
+long long ccb_photo_pose_partials_floats(const ccb_photo_desc* d);
+int ccb_photo_loss_fwd(const ccb_photo_desc* d, ccb_stream_t stream);
+int ccb_photo_loss_bwd(const ccb_photo_desc* d, ccb_stream_t stream);
+int ccb_consensus_targets(const ccb_photo_desc* d, ccb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone warp layer (the functions train.py:22 imports by name).
+ * ---------------------------------------------------------------------------------------------- */
+/* inverse_warp (inverse_warp.py:250-283): img [B,3,h,w], depth [B,h,w], pose [B,6] with row stride
+ * pose_stride floats, K/Kinv [B,3,3] (already scaled by the caller) -> out [B,3,h,w]. */
+int ccb_inverse_warp_fwd(const float* img, const float* depth, const float* pose, int pose_stride,
+                         const float* K, const float* Kinv, int B, int h, int w, int rotation_mode,
+                         int padding_mode, float* out, ccb_stream_t stream);
+/* grads wrt depth [B,h,w] and pose [B,6] (contiguous); pose_partials: B*ntiles*12 floats. */
+int ccb_inverse_warp_bwd(const float* img, const float* depth, const float* pose, int pose_stride,
+                         const float* K, const float* Kinv, int B, int h, int w, int rotation_mode,
+                         int padding_mode, const float* grad_out, float* d_depth, float* d_pose,
+                         float* pose_partials, ccb_stream_t stream);
+long long ccb_warp_pose_partials_floats(int B, int h, int w);
+/* flow_warp (inverse_warp.py:164-192): img [B,C,h,w], flow [B,2,h,w]; padding zeros|border. */
+int ccb_flow_warp_fwd(const float* img, const float* flow, int B, int C, int h, int w,
+                      int padding_mode, float* out, ccb_stream_t stream);
+/* d_flow [B,2,h,w] (may be NULL), d_img [B,C,h,w] (may be NULL; must be zero-filled by the caller). */
+int ccb_flow_warp_bwd(const float* img, const float* flow, int B, int C, int h, int w,
+                      int padding_mode, const float* grad_out, float* d_flow, float* d_img,
+                      ccb_stream_t stream);
+/* pose2flow (inverse_warp.py:195-220): -> flow [B,2,h,w]; padding_mode CCB_PAD_NONE | CCB_PAD_ZEROS. */
+int ccb_pose2flow_fwd(const float* depth, const float* pose, int pose_stride, const float* K,
+                      const float* Kinv, int B, int h, int w, int rotation_mode, int padding_mode,
+                      float* flow, ccb_stream_t stream);
+int ccb_pose2flow_bwd(const float* depth, const float* pose, int pose_stride, const float* K,
+                      const float* Kinv, int B, int h, int w, int rotation_mode, int padding_mode,
+                      const float* grad_flow, float* d_depth, float* d_pose, float* pose_partials,
+                      ccb_stream_t stream);
+
+/* ssim map (ssim.py:68-76, window 13, sigma 1.5, zero padding): img1,img2,out [planes,h,w]. */
+int ccb_ssim_fwd(const float* img1, const float* img2, int planes, int h, int w, const float* taps_host,
+                 float* out, ccb_stream_t stream);
+/* d_img1/d_img2 may be NULL; work: 5*planes*h*w floats. */
+int ccb_ssim_bwd(const float* img1, const float* img2, int planes, int h, int w, const float* taps_host,
+                 const float* grad_out, float* d_img1, float* d_img2, float* work, ccb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Smoothness (loss_functions.py:287-341) for a list of predictions [B,C,h_l,w_l].
+ *   kind CCB_SMOOTH_EDGE   : edge_aware_smoothness_loss(img, pred): needs img[l] = pooled tgt [B,3,h,w]
+ *   kind CCB_SMOOTH_SECOND : smooth_loss(pred), level weight 1/2.3^l
+ * ---------------------------------------------------------------------------------------------- */
+enum { CCB_SMOOTH_EDGE = 0, CCB_SMOOTH_SECOND = 1 };
+typedef struct ccb_smooth_desc {
+    int kind, B, C, nlevels;
+    int h[CCB_MAX_LEVELS], w[CCB_MAX_LEVELS];
+    const float* img[CCB_MAX_LEVELS];
+    const float* pred[CCB_MAX_LEVELS];
+    float* partials;          /* [ccb_smooth_partials_floats()] */
+    float* loss;              /* [1] */
+    const float* grad_out;    /* [1] */
+    float* d_pred[CCB_MAX_LEVELS];
+} ccb_smooth_desc;
+long long ccb_smooth_partials_floats(const ccb_smooth_desc* d);
+int ccb_smooth_fwd(const ccb_smooth_desc* d, ccb_stream_t stream);
+int ccb_smooth_bwd(const ccb_smooth_desc* d, ccb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mask cross-entropies.
+ *   kind CCB_BCE_ONES     : explainability_loss (loss_functions.py:148-155): BCE(mask, 1) per level
+ *   kind CCB_BCE_CONSENSUS: consensus_depth_flow_mask + weighted_binary_cross_entropy
+ *                           (loss_functions.py:221-261)
+ * ---------------------------------------------------------------------------------------------- */
+enum { CCB_BCE_ONES = 0, CCB_BCE_CONSENSUS = 1 };
+typedef struct ccb_bce_desc {
+    int kind, B, C, nlevels;  /* C = mask channels (4) */
+    int h[CCB_MAX_LEVELS], w[CCB_MAX_LEVELS];
+    float thresh, wbce;
+    const float* mask[CCB_MAX_LEVELS];        /* [B,C,h,w] */
+    const float* census_bwd[CCB_MAX_LEVELS];  /* [B,2,h,w] |cam_flow_bwd - flow_bwd| */
+    const float* census_fwd[CCB_MAX_LEVELS];  /* [B,2,h,w] */
+    const float* target_bwd[CCB_MAX_LEVELS];  /* [B,1,h,w] */
+    const float* target_fwd[CCB_MAX_LEVELS];  /* [B,1,h,w] */
+    float* partials;
+    float* loss;
+    const float* grad_out;
+    float* d_mask[CCB_MAX_LEVELS];
+} ccb_bce_desc;
+long long ccb_bce_partials_floats(const ccb_bce_desc* d);
+int ccb_bce_fwd(const ccb_bce_desc* d, ccb_stream_t stream);
+int ccb_bce_bwd(const ccb_bce_desc* d, ccb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCB200_H */

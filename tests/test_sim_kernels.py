@@ -1,0 +1,31 @@
+"""The product kernel sources, compiled by g++ against the CPU execution-model simulator
+(tests/sim), checked against the oracle and the golden fixtures - so that indexing / reduction /
+derivation bugs are caught in the GPU-less container.  The same cases run on the real B200 in
+tests/test_gpu_parity.py."""
+import os
+import sys
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'sim'))
+
+
+@pytest.fixture(scope='module', autouse=True)
+def sim_lib():
+    import build_sim
+    from cc_b200 import _lib, pyramid
+    prev = (_lib._lib, _lib._is_sim)
+    _lib.use_library(build_sim.build())
+    assert _lib.is_simulator()
+    pyramid.clear()
+    yield
+    _lib._lib, _lib._is_sim = prev
+    pyramid.clear()
+
+
+from tests import kernel_cases as KC   # noqa: E402
+
+
+@pytest.mark.parametrize('case', KC.ALL_CASES, ids=lambda f: f.__name__)
+def test_case(case):
+    case(torch.device('cpu'))

@@ -59,6 +59,15 @@ class BceDesc(C.Structure):
     ]
 
 
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ('B', 'Ci', 'Hi', 'Wi', 'Co', 'Ho', 'Wo', 'kh', 'kw', 'stride', 'pad', 'act')] + \
+               [('slope', C.c_float), ('impl', C.c_int)]
+
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
+CONV_FPROP, CONV_DGRAD, CONV_WGRAD = 0, 1, 2
+IMPL_AUTO, IMPL_FFMA, IMPL_TC = 0, 1, 2
+
 _lib = None
 _is_sim = False
 DEFAULT_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libccb200.so')
@@ -89,6 +98,17 @@ _SIGS = {
     'ccb_bce_partials_floats': (_LL, [C.POINTER(BceDesc)]),
     'ccb_bce_fwd': (_I, [C.POINTER(BceDesc), _P]),
     'ccb_bce_bwd': (_I, [C.POINTER(BceDesc), _P]),
+    'ccb_conv_workspace_floats': (_LL, [C.POINTER(ConvDesc), _I]),
+    'ccb_conv2d_fprop': (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _LL, _P]),
+    'ccb_conv2d_dgrad': (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _LL, _P]),
+    'ccb_conv2d_wgrad': (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _LL, _P]),
+    'ccb_act_bwd': (_I, [_P, _P, _P, _LL, _I, _F, _P]),
+    'ccb_bias_grad': (_I, [_P, _P, _I, _I, _I, _P]),
+    'ccb_bn_fwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P]),
+    'ccb_bn_bwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    'ccb_upsample2x_fwd': (_I, [_P, _P, _I, _I, _I, _P]),
+    'ccb_upsample2x_bwd': (_I, [_P, _P, _I, _I, _I, _P]),
+    'ccb_adam_step': (_I, [_P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _F, _P]),
 }
 # entry points added by later translation units register themselves here (conv, nets, optimiser ...)
 EXTRA_SIGS = {}

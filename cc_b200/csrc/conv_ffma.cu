@@ -1,0 +1,418 @@
+// conv_ffma.cu - CUDA-core (FFMA) implicit-GEMM convolution: forward, data-gradient (also the
+// ConvTranspose2d forward) and weight-gradient, with fused bias / residual / activation epilogues.
+//
+// Role: (a) exact-fp32 baseline and fallback for shapes the tcgen05 path does not take (C_in = 3,
+// C_out <= 4 heads, tiny deep levels), (b) numerical cross-check for the tensor-core kernels
+// (conv_tc.cu).  Replaces the cuDNN calls behind nn.Conv2d / nn.ConvTranspose2d in
+// models/{DispResNet6,PoseNetB6,MaskNet6,back2future}.py.
+//
+// GEMM views (NCHW fp32, weights [Co,Ci,kh,kw]):
+//   FPROP : C[m=(b,oy,ox)][n=co]      = sum_k A[m][k=(ci,ky,kx)] * W[co][k]
+//   DGRAD : C[m=(b,jy,jx)][n=ci]      = sum_k dy[b,co,oy,ox] * W[co][ci][ky][kx], one launch per
+//           stride-parity class (py,px): only the taps that hit integer output coordinates are
+//           enumerated, so stride-2 layers waste no MACs.  ConvTranspose2d forward == DGRAD.
+//   WGRAD : C[m=(ci,ky,kx)][n=co]     = sum_k=(b,oy,ox) x[...] * dy[b,co,oy,ox], split-K.
+#include "ccb_common.cuh"
+
+namespace ccb {
+
+enum { MODE_FPROP = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
+
+struct ConvArgs {
+    const float* x;      // FPROP/WGRAD: input activations [B,Ci,Hi,Wi];  DGRAD: unused
+    const float* w;      // [Co,Ci,kh,kw]
+    const float* dy;     // DGRAD/WGRAD: [B,Co,Ho,Wo]
+    const float* bias;   // epilogue (FPROP: per co, DGRAD-as-forward: per ci) or null
+    const float* res;    // residual added before the activation (same layout as out) or null
+    float* out;          // FPROP: y [B,Co,Ho,Wo]; DGRAD: dx [B,Ci,Hi,Wi]; WGRAD: dw [Co,Ci,kh,kw]
+    float* work;         // split-K partials [splits][numel(out)]
+    int B, Ci, Hi, Wi, Co, Ho, Wo, kh, kw, stride, pad;
+    int act;             // CCB_ACT_*
+    float slope;
+    int splits;
+    // DGRAD parity class
+    int py, px, Hc, Wc, ky0, kx0, nky, nkx;
+    int M, N, K;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    switch (act) {
+        case CCB_ACT_RELU: return fmaxf(v, 0.f);
+        case CCB_ACT_LEAKY: return v > 0.f ? v : v * slope;
+        case CCB_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        default: return v;
+    }
+}
+
+// Tile configuration: BM x BN outputs per CTA, TM x TN per thread, 256 threads, BK = 16.
+template <int BM_, int BN_, int TM_, int TN_>
+struct Cfg {
+    static constexpr int BM = BM_, BN = BN_, TM = TM_, TN = TN_, BK = 16, NT = 256;
+    static_assert((BM / TM) * (BN / TN) == NT, "thread tiling must cover the CTA tile");
+};
+
+// Decoded K index (one per k of the current tile), filled cooperatively.
+struct KInfo { int off; int a; int b; int off2; };
+
+template <int MODE>
+__device__ __forceinline__ KInfo decode_k(const ConvArgs& a, int k) {
+    KInfo r;
+    r.off = -1; r.a = 0; r.b = 0; r.off2 = 0;
+    if (k >= a.K) return r;
+    if (MODE == MODE_FPROP) {
+        int kk = a.kh * a.kw;
+        int ci = k / kk, rem = k - ci * kk;
+        int ky = rem / a.kw, kx = rem - ky * a.kw;
+        r.off = ci * a.Hi * a.Wi; r.a = ky; r.b = kx; r.off2 = 0;
+    } else if (MODE == MODE_DGRAD) {
+        int nt = a.nky * a.nkx;
+        int co = k / nt, rem = k - co * nt;
+        int tky = rem / a.nkx, tkx = rem - tky * a.nkx;
+        int ky = a.ky0 + tky * a.stride, kx = a.kx0 + tkx * a.stride;
+        if (ky >= a.kh || kx >= a.kw) return r;          // parity class without a valid tap
+        r.off = co * a.Ho * a.Wo; r.a = ky; r.b = kx;
+        r.off2 = co * a.Ci * a.kh * a.kw + ky * a.kw + kx;
+    } else {
+        int hw = a.Ho * a.Wo;
+        int b = k / hw, rem = k - b * hw;
+        int oy = rem / a.Wo, ox = rem - oy * a.Wo;
+        r.off = b; r.a = oy; r.b = ox; r.off2 = 0;
+    }
+    return r;
+}
+
+// Per-thread decoded M index (fixed across the K loop).
+struct MInfo { int valid; int b; int y; int x; int c; };
+
+template <int MODE>
+__device__ __forceinline__ MInfo decode_m(const ConvArgs& a, int m) {
+    MInfo r;
+    r.valid = m < a.M; r.b = r.y = r.x = r.c = 0;
+    if (!r.valid) return r;
+    if (MODE == MODE_FPROP) {
+        int hw = a.Ho * a.Wo;
+        r.b = m / hw;
+        int rem = m - r.b * hw;
+        r.y = rem / a.Wo; r.x = rem - r.y * a.Wo;
+    } else if (MODE == MODE_DGRAD) {
+        int hw = a.Hc * a.Wc;
+        r.b = m / hw;
+        int rem = m - r.b * hw;
+        int jy = rem / a.Wc, jx = rem - jy * a.Wc;
+        r.y = a.py + jy * a.stride; r.x = a.px + jx * a.stride;
+    } else {
+        int kk = a.kh * a.kw;
+        r.c = m / kk;
+        int rem = m - r.c * kk;
+        r.y = rem / a.kw; r.x = rem - r.y * a.kw;   // (ky, kx)
+    }
+    return r;
+}
+
+template <int MODE>
+__device__ __forceinline__ float fetch_a(const ConvArgs& a, const MInfo& mi, const KInfo& ki) {
+    if (!mi.valid || ki.off < 0) return 0.f;
+    if (MODE == MODE_FPROP) {
+        int iy = mi.y * a.stride - a.pad + ki.a, ix = mi.x * a.stride - a.pad + ki.b;
+        if (iy < 0 || iy >= a.Hi || ix < 0 || ix >= a.Wi) return 0.f;
+        return __ldg(a.x + (long long)mi.b * a.Ci * a.Hi * a.Wi + ki.off + iy * a.Wi + ix);
+    } else if (MODE == MODE_DGRAD) {
+        int ty = mi.y + a.pad - ki.a, tx = mi.x + a.pad - ki.b;     // divisible by stride by construction
+        int oy = ty / a.stride, ox = tx / a.stride;
+        if (ty < 0 || tx < 0 || oy >= a.Ho || ox >= a.Wo) return 0.f;
+        return __ldg(a.dy + (long long)mi.b * a.Co * a.Ho * a.Wo + ki.off + oy * a.Wo + ox);
+    } else {
+        int iy = ki.a * a.stride - a.pad + mi.y, ix = ki.b * a.stride - a.pad + mi.x;
+        if (iy < 0 || iy >= a.Hi || ix < 0 || ix >= a.Wi) return 0.f;
+        return __ldg(a.x + ((long long)ki.off * a.Ci + mi.c) * a.Hi * a.Wi + iy * a.Wi + ix);
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ float fetch_b(const ConvArgs& a, const KInfo& ki, int k, int n) {
+    if (n >= a.N || ki.off < 0) return 0.f;
+    if (MODE == MODE_FPROP) return __ldg(a.w + (long long)n * a.K + k);
+    if (MODE == MODE_DGRAD) return __ldg(a.w + ki.off2 + (long long)n * a.kh * a.kw);
+    return __ldg(a.dy + ((long long)ki.off * a.Co + n) * a.Ho * a.Wo + ki.a * a.Wo + ki.b);
+}
+
+// linear offset of output element (m, n) in `out`
+template <int MODE>
+__device__ __forceinline__ long long out_offset(const ConvArgs& a, const MInfo& mi, int m, int n) {
+    if (MODE == MODE_FPROP) return ((long long)mi.b * a.Co + n) * a.Ho * a.Wo + mi.y * a.Wo + mi.x;
+    if (MODE == MODE_DGRAD) return ((long long)mi.b * a.Ci + n) * a.Hi * a.Wi + mi.y * a.Wi + mi.x;
+    return (long long)n * a.M + m;   // dw[co][(ci,ky,kx)]
+}
+
+template <int MODE, class C>
+__global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvArgs a) {
+    constexpr int BM = C::BM, BN = C::BN, BK = C::BK, TM = C::TM, TN = C::TN;
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    __shared__ KInfo s_k[2][BK];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // K range of this split (in tiles)
+    const int ktiles = cdiv(a.K, BK);
+    const int per = cdiv(ktiles, a.splits);
+    const int kt_beg = blockIdx.z * per, kt_end = min(ktiles, kt_beg + per);
+
+    // loader mapping: A element (kk = tid / BM + e * (256 / BM), m = tid % BM)
+    constexpr int A_E = BM * BK / 256, A_KSTEP = 256 / BM;
+    constexpr int B_E = BN * BK / 256;
+    const int am = tid % BM, ak0 = tid / BM;
+    const MInfo ami = decode_m<MODE>(a, m0 + am);
+    const int bk = tid % BK, bn0 = tid / BK;     // B element (kk = bk, n = bn0 + e * 16)
+
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    if (tid < BK && kt_beg < kt_end) s_k[0][tid] = decode_k<MODE>(a, kt_beg * BK + tid);
+    __syncthreads();
+    int buf = 0;
+    for (int kt = kt_beg; kt < kt_end; ++kt) {
+        const int k0 = kt * BK;
+#pragma unroll
+        for (int e = 0; e < A_E; ++e) {
+            int kk = ak0 + e * A_KSTEP;
+            As[kk][am] = fetch_a<MODE>(a, ami, s_k[buf][kk]);
+        }
+#pragma unroll
+        for (int e = 0; e < B_E; ++e) {
+            int n = bn0 + e * (256 / BK);
+            Bs[bk][n] = fetch_b<MODE>(a, s_k[buf][bk], k0 + bk, n0 + n);
+        }
+        __syncthreads();
+        if (tid < BK && kt + 1 < kt_end) s_k[buf ^ 1][tid] = decode_k<MODE>(a, (kt + 1) * BK + tid);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float av[TM], bv[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+
+    // epilogue
+    const long long out_numel = (MODE == MODE_FPROP) ? (long long)a.B * a.Co * a.Ho * a.Wo
+                              : (MODE == MODE_DGRAD) ? (long long)a.B * a.Ci * a.Hi * a.Wi
+                                                     : (long long)a.M * a.N;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int m = m0 + ty * TM + i;
+        if (m >= a.M) continue;
+        MInfo mi = decode_m<MODE>(a, m);
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            int n = n0 + tx * TN + j;
+            if (n >= a.N) continue;
+            long long o = out_offset<MODE>(a, mi, m, n);
+            float v = acc[i][j];
+            if (a.splits > 1) {
+                a.work[(long long)blockIdx.z * out_numel + o] = v;
+            } else {
+                if (MODE != MODE_WGRAD) {
+                    if (a.bias) v += __ldg(a.bias + n);
+                    if (a.res) v += __ldg(a.res + o);
+                    v = apply_act(v, a.act, a.slope);
+                }
+                a.out[o] = v;
+            }
+        }
+    }
+}
+
+// out[i] = epilogue(sum_s work[s][i]);  channel = (i / plane) % C for the bias
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ work, float* __restrict__ out,
+                                                            const float* __restrict__ bias, const float* __restrict__ res,
+                                                            long long numel, int splits, int plane, int C, int act,
+                                                            float slope) {
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= numel) return;
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += __ldg(work + (long long)s * numel + i);
+    if (bias) v += __ldg(bias + (int)((i / plane) % C));
+    if (res) v += __ldg(res + i);
+    out[i] = apply_act(v, act, slope);
+}
+
+// dz = dy * act'(y)  (in terms of the activation OUTPUT y), optionally accumulating a second grad
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                      float* __restrict__ dz, long long numel, int act, float slope) {
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= numel) return;
+    float g = __ldg(dy + i), yv = __ldg(y + i);
+    switch (act) {
+        case CCB_ACT_RELU: g = (yv > 0.f) ? g : 0.f; break;
+        case CCB_ACT_LEAKY: g = (yv > 0.f) ? g : g * slope; break;
+        case CCB_ACT_SIGMOID: g = g * yv * (1.f - yv); break;
+        default: break;
+    }
+    dz[i] = g;
+}
+
+// db[c] = sum_{b,y,x} dy[b,c,y,x] : one CTA per channel, fixed-order two-level sum
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int B,
+                                                        int C, int plane) {
+    __shared__ float s_red[32];
+    const int c = blockIdx.x;
+    float v[1] = {0.f};
+    for (int b = 0; b < B; ++b) {
+        const float* p = dy + ((long long)b * C + c) * plane;
+        for (int i = threadIdx.x; i < plane; i += 256) v[0] += __ldg(p + i);
+    }
+    block_sum<1>(v, s_red);
+    if (threadIdx.x == 0) db[c] = v[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+static int pick_splits(int tiles, int ktiles, int max_splits) {
+    const int target = 148 * 4;
+    if (tiles >= target || ktiles <= 2) return 1;
+    int s = target / tiles;
+    if (s > ktiles / 2) s = ktiles / 2;
+    if (s > max_splits) s = max_splits;
+    return s < 1 ? 1 : s;
+}
+
+template <int MODE>
+static int launch_gemm(ConvArgs& a, long long out_numel, long long work_floats, cudaStream_t st, const char* what) {
+    const bool narrow = a.N <= 16;
+    const int BM = narrow ? 128 : 64, BN = narrow ? 16 : 64;
+    const int mt = cdiv(a.M, BM), nt = cdiv(a.N, BN), ktiles = cdiv(a.K, 16);
+    int max_splits = (a.work && out_numel > 0) ? (int)(work_floats / out_numel) : 1;
+    if (max_splits > 64) max_splits = 64;
+    a.splits = pick_splits(mt * nt, ktiles, max_splits);
+    // make sure no split is empty
+    while (a.splits > 1 && cdiv(ktiles, a.splits) * (a.splits - 1) >= ktiles) --a.splits;
+    dim3 grid(mt, nt, a.splits);
+    auto k_narrow = conv_gemm_kernel<MODE, Cfg<128, 16, 8, 1>>;
+    auto k_wide = conv_gemm_kernel<MODE, Cfg<64, 64, 4, 4>>;
+    if (narrow) CCB_LAUNCH(k_narrow, grid, dim3(256), 0, st, a);
+    else CCB_LAUNCH(k_wide, grid, dim3(256), 0, st, a);
+    int rc = check_launch(what);
+    if (rc) return rc;
+    if (a.splits > 1) {
+        int plane = (MODE == MODE_FPROP) ? a.Ho * a.Wo : (MODE == MODE_DGRAD) ? a.Hi * a.Wi : 1;
+        int C = (MODE == MODE_FPROP) ? a.Co : (MODE == MODE_DGRAD) ? a.Ci : 1;
+        CCB_LAUNCH(splitk_reduce_kernel, dim3((unsigned)((out_numel + 255) / 256)), dim3(256), 0, st,
+                   a.work, a.out, (MODE == MODE_WGRAD) ? nullptr : a.bias, (MODE == MODE_WGRAD) ? nullptr : a.res,
+                   out_numel, a.splits, plane, C, (MODE == MODE_WGRAD) ? CCB_ACT_NONE : a.act, a.slope);
+        rc = check_launch("splitk_reduce");
+    }
+    return rc;
+}
+
+static int fill_conv(ConvArgs& a, const ccb_conv_desc* d) {
+    CCB_REQUIRE(d != nullptr, CCB_ERR_ARG, "conv: null descriptor");
+    CCB_REQUIRE(d->B >= 1 && d->Ci >= 1 && d->Co >= 1 && d->Hi >= 1 && d->Wi >= 1, CCB_ERR_ARG, "conv: bad sizes");
+    CCB_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->stride >= 1 && d->pad >= 0, CCB_ERR_ARG, "conv: bad kernel/stride/pad");
+    CCB_REQUIRE(d->Ho >= 1 && d->Wo >= 1, CCB_ERR_ARG, "conv: bad output size");
+    // consistency of (Hi, Ho): Hi may exceed the minimal size by up to stride-1 (ConvTranspose output_padding)
+    CCB_REQUIRE((d->Hi + 2 * d->pad - d->kh) / d->stride + 1 == d->Ho && (d->Wi + 2 * d->pad - d->kw) / d->stride + 1 == d->Wo,
+                CCB_ERR_ARG, "conv: Ho/Wo inconsistent with Hi/Wi (%d,%d -> %d,%d, k %d s %d p %d)", d->Hi, d->Wi, d->Ho,
+                d->Wo, d->kh, d->stride, d->pad);
+    memset(&a, 0, sizeof(a));
+    a.B = d->B; a.Ci = d->Ci; a.Hi = d->Hi; a.Wi = d->Wi; a.Co = d->Co; a.Ho = d->Ho; a.Wo = d->Wo;
+    a.kh = d->kh; a.kw = d->kw; a.stride = d->stride; a.pad = d->pad;
+    a.act = d->act; a.slope = d->slope; a.splits = 1;
+    return CCB_OK;
+}
+
+}  // namespace ccb
+
+using namespace ccb;
+
+extern "C" long long ccb_conv_workspace_floats(const ccb_conv_desc* d, int op) {
+    if (!d) return -1;
+    long long numel = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Co * d->Ho * d->Wo
+                    : (op == CCB_CONV_DGRAD) ? (long long)d->B * d->Ci * d->Hi * d->Wi
+                                             : (long long)d->Co * d->Ci * d->kh * d->kw;
+    // enough for up to 16 splits, capped at 64 MiB of floats
+    long long cap = 16ll * 1024 * 1024;
+    long long want = numel * 16;
+    if (want > cap) want = (cap / numel) * numel;
+    return want < numel ? 0 : want;
+}
+
+extern "C" int ccb_conv2d_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float* bias,
+                                const float* res, float* y, float* work, long long work_floats, ccb_stream_t stream) {
+    ConvArgs a;
+    int rc = fill_conv(a, d);
+    if (rc) return rc;
+    CCB_REQUIRE(x && w && y, CCB_ERR_ARG, "conv2d_fprop: null pointer");
+    a.x = x; a.w = w; a.bias = bias; a.res = res; a.out = y; a.work = work;
+    a.M = a.B * a.Ho * a.Wo; a.N = a.Co; a.K = a.Ci * a.kh * a.kw;
+    return launch_gemm<MODE_FPROP>(a, (long long)a.M * a.N, work_floats, (cudaStream_t)stream, "conv2d_fprop");
+}
+
+// dx[B,Ci,Hi,Wi] = conv_transpose(dy, w); with bias/res/act this is the ConvTranspose2d forward.
+extern "C" int ccb_conv2d_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const float* bias,
+                                const float* res, float* dx, float* work, long long work_floats, ccb_stream_t stream) {
+    ConvArgs a;
+    int rc = fill_conv(a, d);
+    if (rc) return rc;
+    CCB_REQUIRE(dy && w && dx, CCB_ERR_ARG, "conv2d_dgrad: null pointer");
+    a.dy = dy; a.w = w; a.bias = bias; a.res = res; a.out = dx; a.work = work;
+    const int s = a.stride;
+    for (int py = 0; py < s && py < a.Hi; ++py)
+        for (int px = 0; px < s && px < a.Wi; ++px) {
+            ConvArgs c = a;
+            c.py = py; c.px = px;
+            c.Hc = (a.Hi - py + s - 1) / s; c.Wc = (a.Wi - px + s - 1) / s;
+            c.ky0 = (py + a.pad) % s; c.kx0 = (px + a.pad) % s;
+            c.nky = (a.kh > c.ky0) ? (a.kh - c.ky0 + s - 1) / s : 0;
+            c.nkx = (a.kw > c.kx0) ? (a.kw - c.kx0 + s - 1) / s : 0;
+            c.M = a.B * c.Hc * c.Wc; c.N = a.Ci; c.K = a.Co * c.nky * c.nkx;
+            if (c.K == 0) { c.K = 1; c.nky = c.nkx = 1; c.ky0 = a.kh; c.kx0 = a.kw; }   // no tap hits: output = epilogue(0)
+            // split-K partials of different parity classes must not alias: no split-K for strided dgrad
+            float* wk = (s == 1) ? work : nullptr;
+            c.work = wk;
+            rc = launch_gemm<MODE_DGRAD>(c, (long long)a.B * a.Ci * a.Hi * a.Wi, wk ? work_floats : 0, (cudaStream_t)stream,
+                                         "conv2d_dgrad");
+            if (rc) return rc;
+        }
+    return CCB_OK;
+}
+
+extern "C" int ccb_conv2d_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw, float* db,
+                                float* work, long long work_floats, ccb_stream_t stream) {
+    ConvArgs a;
+    int rc = fill_conv(a, d);
+    if (rc) return rc;
+    CCB_REQUIRE(x && dy && dw, CCB_ERR_ARG, "conv2d_wgrad: null pointer");
+    a.x = x; a.dy = dy; a.out = dw; a.work = work; a.act = CCB_ACT_NONE;
+    a.M = a.Ci * a.kh * a.kw; a.N = a.Co; a.K = a.B * a.Ho * a.Wo;
+    rc = launch_gemm<MODE_WGRAD>(a, (long long)a.M * a.N, work_floats, (cudaStream_t)stream, "conv2d_wgrad");
+    if (rc) return rc;
+    if (db) {
+        CCB_LAUNCH(bias_grad_kernel, dim3(a.Co), dim3(256), 0, stream, dy, db, a.B, a.Co, a.Ho * a.Wo);
+        rc = check_launch("bias_grad");
+    }
+    return rc;
+}
+
+extern "C" int ccb_act_bwd(const float* dy, const float* y, float* dz, long long numel, int act, float slope,
+                           ccb_stream_t stream) {
+    CCB_REQUIRE(dy && y && dz && numel >= 0, CCB_ERR_ARG, "act_bwd: null pointer");
+    if (numel == 0) return CCB_OK;
+    CCB_LAUNCH(act_bwd_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), 0, stream, dy, y, dz, numel, act, slope);
+    return check_launch("act_bwd");
+}
+
+extern "C" int ccb_bias_grad(const float* dy, float* db, int B, int C, int plane, ccb_stream_t stream) {
+    CCB_REQUIRE(dy && db, CCB_ERR_ARG, "bias_grad: null pointer");
+    CCB_LAUNCH(bias_grad_kernel, dim3(C), dim3(256), 0, stream, dy, db, B, C, plane);
+    return check_launch("bias_grad");
+}

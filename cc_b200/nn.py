@@ -1,0 +1,279 @@
+"""Layer primitives of the four networks on the libccb200 kernels: Conv2d / ConvTranspose2d with fused
+bias + residual + activation epilogues, BatchNorm2d, bilinear x2 upsampling - each a
+torch.autograd.Function over hand-written forward / data-gradient / weight-gradient kernels.
+
+Parameter names and shapes equal torch's nn.Conv2d / nn.ConvTranspose2d / nn.BatchNorm2d, so the
+reference's checkpoints (utils.py:55-63) load unchanged.  No cuDNN / ATen compute on this path."""
+import ctypes as C
+import math
+import torch
+from torch import nn
+from . import _lib
+
+ACT = {None: _lib.ACT_NONE, 'none': _lib.ACT_NONE, 'relu': _lib.ACT_RELU, 'leaky': _lib.ACT_LEAKY,
+       'sigmoid': _lib.ACT_SIGMOID}
+CONV_IMPL = _lib.IMPL_AUTO          # tests flip this to force the FFMA or the tcgen05 path
+
+_WORK = {}
+
+
+def _workspace(dev, floats):
+    """One grow-only scratch buffer per device (split-K partials); stream-ordered reuse."""
+    if floats <= 0:
+        return None, 0
+    buf = _WORK.get(dev)
+    if buf is None or buf.numel() < floats:
+        buf = torch.empty(int(floats), device=dev, dtype=torch.float32)
+        _WORK[dev] = buf
+    return buf, buf.numel()
+
+
+def _desc(B, Ci, Hi, Wi, Co, Ho, Wo, k, stride, pad, act, slope):
+    d = _lib.ConvDesc()
+    d.B, d.Ci, d.Hi, d.Wi, d.Co, d.Ho, d.Wo = B, Ci, Hi, Wi, Co, Ho, Wo
+    d.kh = d.kw = k
+    d.stride, d.pad, d.act, d.slope, d.impl = stride, pad, act, slope, CONV_IMPL
+    return d
+
+
+def _c(t):
+    return _lib.contig(t.detach())
+
+
+def _run(op, d, *args):
+    lib = _lib.lib()
+    dev = args[0].device
+    work, wf = _workspace(dev, lib.ccb_conv_workspace_floats(C.byref(d), op))
+    fn = (lib.ccb_conv2d_fprop, lib.ccb_conv2d_dgrad, lib.ccb_conv2d_wgrad)[op]
+    ptrs = [_lib.ptr(a) for a in args]
+    _lib.check(fn(C.byref(d), *ptrs, _lib.ptr(work), wf, _lib.stream(args[0])), 'conv op %d' % op)
+
+
+def _act_bwd(g, y, act, slope):
+    if act == _lib.ACT_NONE:
+        return g
+    dz = torch.empty_like(g)
+    _lib.check(_lib.lib().ccb_act_bwd(_lib.ptr(g), _lib.ptr(y), _lib.ptr(dz), g.numel(), act, slope, _lib.stream(g)),
+               'act_bwd')
+    return dz
+
+
+class _Conv2dFn(torch.autograd.Function):
+    """y = act(conv2d(x, w) + bias + res)"""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, res, stride, pad, act, slope):
+        x, w = _c(x), _c(w)
+        bias = _c(bias) if bias is not None else None
+        res = _c(res) if res is not None else None
+        B, Ci, Hi, Wi = x.shape
+        Co, _, k, _ = w.shape
+        Ho, Wo = (Hi + 2 * pad - k) // stride + 1, (Wi + 2 * pad - k) // stride + 1
+        y = torch.empty(B, Co, Ho, Wo, device=x.device, dtype=torch.float32)
+        d = _desc(B, Ci, Hi, Wi, Co, Ho, Wo, k, stride, pad, act, slope)
+        _run(_lib.CONV_FPROP, d, x, w, bias, res, y)
+        ctx.save_for_backward(x, w, y if act != _lib.ACT_NONE else None)
+        ctx.cfg = (stride, pad, act, slope, bias is not None, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, y = ctx.saved_tensors
+        stride, pad, act, slope, has_bias, has_res = ctx.cfg
+        B, Ci, Hi, Wi = x.shape
+        Co, _, k, _ = w.shape
+        dz = _act_bwd(_c(g), y, act, slope)
+        d = _desc(B, Ci, Hi, Wi, Co, dz.shape[2], dz.shape[3], k, stride, pad, _lib.ACT_NONE, 0.0)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _run(_lib.CONV_DGRAD, d, dz, w, None, None, dx)
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            dw = torch.empty_like(w)
+            db = torch.empty(Co, device=x.device) if has_bias else None
+            _run(_lib.CONV_WGRAD, d, x, dz, dw, db)
+        return dx, dw, db, (dz if has_res else None), None, None, None, None
+
+
+class _ConvT2dFn(torch.autograd.Function):
+    """y = act(conv_transpose2d(x, w) + bias); torch weight layout [Cin, Cout, k, k].
+    Forward is the data-gradient kernel of the conv (Co=Cin, Ci=Cout) - SURVEY.md K7."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, pad, out_pad, act, slope):
+        x, w = _c(x), _c(w)
+        bias = _c(bias) if bias is not None else None
+        B, Cin, h, wd = x.shape
+        _, Cout, k, _ = w.shape
+        H = (h - 1) * stride - 2 * pad + k + out_pad
+        W = (wd - 1) * stride - 2 * pad + k + out_pad
+        y = torch.empty(B, Cout, H, W, device=x.device, dtype=torch.float32)
+        d = _desc(B, Cout, H, W, Cin, h, wd, k, stride, pad, act, slope)
+        _run(_lib.CONV_DGRAD, d, x, w, bias, None, y)
+        ctx.save_for_backward(x, w, y if act != _lib.ACT_NONE else None)
+        ctx.cfg = (stride, pad, act, slope, bias is not None, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, y = ctx.saved_tensors
+        stride, pad, act, slope, has_bias, H, W = ctx.cfg
+        B, Cin, h, wd = x.shape
+        _, Cout, k, _ = w.shape
+        dz = _act_bwd(_c(g), y, act, slope)
+        d = _desc(B, Cout, H, W, Cin, h, wd, k, stride, pad, _lib.ACT_NONE, 0.0)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _run(_lib.CONV_FPROP, d, dz, w, None, None, dx)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            _run(_lib.CONV_WGRAD, d, dz, x, dw, None)        # roles swapped: activations = dz, grads = x
+        if has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(Cout, device=x.device)
+            _lib.check(_lib.lib().ccb_bias_grad(_lib.ptr(dz), _lib.ptr(db), B, Cout, H * W, _lib.stream(dz)), 'bias_grad')
+        return dx, dw, db, None, None, None, None, None
+
+
+class _BatchNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, rm, rv, training, eps, momentum):
+        x, gamma, beta = _c(x), _c(gamma), _c(beta)
+        B, Cc, h, w = x.shape
+        y = torch.empty_like(x)
+        stats = torch.empty(Cc, 2, device=x.device) if training else None
+        _lib.check(_lib.lib().ccb_bn_fwd(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(y), _lib.ptr(stats),
+                                         _lib.ptr(rm), _lib.ptr(rv), B, Cc, h * w, eps, momentum, int(training),
+                                         _lib.stream(x)), 'bn_fwd')
+        ctx.save_for_backward(x, gamma, stats)
+        ctx.training = training
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, gamma, stats = ctx.saved_tensors
+        if not ctx.training:
+            raise NotImplementedError('cc_b200: BatchNorm backward is implemented for training mode only')
+        B, Cc, h, w = x.shape
+        g = _c(g)
+        dx, dg, db = torch.empty_like(x), torch.empty_like(gamma), torch.empty_like(gamma)
+        _lib.check(_lib.lib().ccb_bn_bwd(_lib.ptr(x), _lib.ptr(g), _lib.ptr(gamma), _lib.ptr(stats), _lib.ptr(dx),
+                                         _lib.ptr(dg), _lib.ptr(db), B, Cc, h * w, _lib.stream(x)), 'bn_bwd')
+        return dx, dg, db, None, None, None, None, None
+
+
+class _Upsample2xFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        B, Cc, h, w = x.shape
+        y = torch.empty(B, Cc, 2 * h, 2 * w, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.lib().ccb_upsample2x_fwd(_lib.ptr(x), _lib.ptr(y), B * Cc, h, w, _lib.stream(x)), 'upsample2x_fwd')
+        ctx.shape = (B, Cc, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        B, Cc, h, w = ctx.shape
+        g = _c(g)
+        dx = torch.empty(B, Cc, h, w, device=g.device, dtype=torch.float32)
+        _lib.check(_lib.lib().ccb_upsample2x_bwd(_lib.ptr(g), _lib.ptr(dx), B * Cc, h, w, _lib.stream(g)), 'upsample2x_bwd')
+        return dx
+
+
+def conv2d(x, w, bias=None, res=None, stride=1, padding=0, act=None, slope=0.0):
+    return _Conv2dFn.apply(x, w, bias, res, stride, padding, ACT[act], slope)
+
+
+def conv_transpose2d(x, w, bias=None, stride=1, padding=0, output_padding=0, act=None, slope=0.0):
+    return _ConvT2dFn.apply(x, w, bias, stride, padding, output_padding, ACT[act], slope)
+
+
+def upsample2x(x):
+    """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False)."""
+    return _Upsample2xFn.apply(x)
+
+
+# -------------------------------------------------------------------------------------------------
+class Conv2d(nn.Module):
+    """nn.Conv2d (square kernel) + optional fused activation; parameters named like torch's."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True, act=None, slope=0.0):
+        super().__init__()
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, kernel_size
+        self.stride, self.padding, self.act, self.slope = stride, padding, act, slope
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels, kernel_size, kernel_size))
+        self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):           # torch's default Conv2d init
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            bound = 1 / math.sqrt(self.in_channels * self.kernel_size ** 2)
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, x, res=None):
+        return conv2d(x, self.weight, self.bias, res, self.stride, self.padding, self.act, self.slope)
+
+
+class ConvTranspose2d(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, bias=True,
+                 act=None, slope=0.0):
+        super().__init__()
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, kernel_size
+        self.stride, self.padding, self.output_padding, self.act, self.slope = stride, padding, output_padding, act, slope
+        self.weight = nn.Parameter(torch.empty(in_channels, out_channels, kernel_size, kernel_size))
+        self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            bound = 1 / math.sqrt(out_channels * kernel_size ** 2)
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, x):
+        return conv_transpose2d(x, self.weight, self.bias, self.stride, self.padding, self.output_padding, self.act,
+                                self.slope)
+
+
+class BatchNorm2d(nn.Module):
+    def __init__(self, num_features, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        self.weight = nn.Parameter(torch.ones(num_features))
+        self.bias = nn.Parameter(torch.zeros(num_features))
+        self.register_buffer('running_mean', torch.zeros(num_features))
+        self.register_buffer('running_var', torch.ones(num_features))
+        self.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
+
+    def forward(self, x):
+        if self.training:
+            self.num_batches_tracked += 1
+        return _BatchNormFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.training,
+                                  self.eps, self.momentum)
+
+
+class Fused(nn.Module):
+    """Parameter-free placeholder for an activation module that is fused into the preceding layer's
+    epilogue; it keeps nn.Sequential indices (hence state_dict keys) identical to the reference."""
+
+    def __init__(self, what='relu'):
+        super().__init__()
+        self.what = what
+
+    def forward(self, x):
+        return x
+
+    def extra_repr(self):
+        return 'fused=' + self.what
+
+
+def xavier_init_(module, bias_uniform=False):
+    """The reference nets' init_weights(): xavier_uniform on (transposed) conv weights, zero bias
+    (Back2Future: U[0,1) bias, back2future.py:106-116)."""
+    for m in module.modules():
+        if isinstance(m, (Conv2d, ConvTranspose2d)):
+            nn.init.xavier_uniform_(m.weight.data)
+            if m.bias is not None:
+                if bias_uniform:
+                    nn.init.uniform_(m.bias.data)
+                else:
+                    m.bias.data.zero_()

@@ -190,6 +190,56 @@ long long ccb_bce_partials_floats(const ccb_bce_desc* d);
 int ccb_bce_fwd(const ccb_bce_desc* d, ccb_stream_t stream);
 int ccb_bce_bwd(const ccb_bce_desc* d, ccb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Convolutions of the four networks (replace the cuDNN calls behind nn.Conv2d / nn.ConvTranspose2d /
+ * nn.BatchNorm2d in models/DispResNet6.py:9-94, PoseNetB6.py:10-21, MaskNet6.py:5-16,
+ * back2future.py:27-48).  NCHW fp32, weights [Co,Ci,kh,kw], square stride/pad.
+ *   y = act(conv(x, w) + bias + res)                               ccb_conv2d_fprop
+ *   dx = act(conv_transpose(dy, w) + bias + res)                   ccb_conv2d_dgrad
+ *        (plain data-gradient when bias/res are NULL and act is NONE; with them it is the
+ *         nn.ConvTranspose2d forward of a layer whose torch weight [Cin_t,Cout_t,k,k] is this w)
+ *   dw = d/dw, db = sum dy                                         ccb_conv2d_wgrad
+ * impl: CCB_CONV_IMPL_AUTO picks tcgen05 tensor-core tiles where the shape allows and the FFMA
+ *       kernels otherwise; _FFMA / _TC force one (tests).
+ * ---------------------------------------------------------------------------------------------- */
+enum { CCB_ACT_NONE = 0, CCB_ACT_RELU = 1, CCB_ACT_LEAKY = 2, CCB_ACT_SIGMOID = 3 };
+enum { CCB_CONV_FPROP = 0, CCB_CONV_DGRAD = 1, CCB_CONV_WGRAD = 2 };
+enum { CCB_CONV_IMPL_AUTO = 0, CCB_CONV_IMPL_FFMA = 1, CCB_CONV_IMPL_TC = 2 };
+typedef struct ccb_conv_desc {
+    int B, Ci, Hi, Wi;      /* input  [B,Ci,Hi,Wi] */
+    int Co, Ho, Wo;         /* output [B,Co,Ho,Wo]; Ho = (Hi + 2 pad - kh) / stride + 1 */
+    int kh, kw, stride, pad;
+    int act;                /* CCB_ACT_* fused into the epilogue */
+    float slope;            /* LeakyReLU negative slope */
+    int impl;               /* CCB_CONV_IMPL_* */
+} ccb_conv_desc;
+long long ccb_conv_workspace_floats(const ccb_conv_desc* d, int op);
+int ccb_conv2d_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float* bias,
+                     const float* res, float* y, float* work, long long work_floats, ccb_stream_t stream);
+int ccb_conv2d_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const float* bias,
+                     const float* res, float* dx, float* work, long long work_floats, ccb_stream_t stream);
+int ccb_conv2d_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw, float* db,
+                     float* work, long long work_floats, ccb_stream_t stream);
+/* dz = dy * act'(.) expressed through the activation OUTPUT y (in place allowed: dz == dy). */
+int ccb_act_bwd(const float* dy, const float* y, float* dz, long long numel, int act, float slope,
+                ccb_stream_t stream);
+int ccb_bias_grad(const float* dy, float* db, int B, int C, int plane, ccb_stream_t stream);
+
+/* BatchNorm2d over [B,C,plane] (DispResNet6.py:45-52).  training: batch statistics, stats[C][2] =
+ * {mean, invstd} saved for backward, running stats updated in place (momentum, unbiased var). */
+int ccb_bn_fwd(const float* x, const float* gamma, const float* beta, float* y, float* stats,
+               float* running_mean, float* running_var, int B, int C, int plane, float eps, float momentum,
+               int training, ccb_stream_t stream);
+int ccb_bn_bwd(const float* x, const float* dy, const float* gamma, const float* stats, float* dx,
+               float* dgamma, float* dbeta, int B, int C, int plane, ccb_stream_t stream);
+/* bilinear x2 upsample, align_corners=False (DispResNet6.py:174; back2future.py:60): [planes,h,w] -> [planes,2h,2w] */
+int ccb_upsample2x_fwd(const float* x, float* y, int planes, int h, int w, ccb_stream_t stream);
+int ccb_upsample2x_bwd(const float* dy, float* dx, int planes, int h, int w, ccb_stream_t stream);
+/* torch.optim.Adam step (train.py:307-310,568) on one flat fp32 buffer; grad_scale pre-multiplies the
+ * gradient (1/world_size after the NCCL all-reduce sum).  `step` is the 1-based step count. */
+int ccb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step,
+                  float lr, float beta1, float beta2, float eps, float grad_scale, ccb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

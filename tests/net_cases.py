@@ -1,0 +1,163 @@
+"""Parity cases for the convolution kernels and the networks (shared by the simulator tests and the
+GPU tests): product modules vs the golden fixtures frozen from the reference and vs the oracle."""
+import torch
+import torch.nn.functional as F
+from tests.util import golden, T, assert_close, key_with_stride, pick
+from cc_b200 import synth, nn as cnn, models as CM
+from oracle import nets as ON
+
+TOL = 1e-4
+
+
+def _wts(shape, seed, device):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed)).to(device)
+
+
+def case_conv_shapes(device, big=False):
+    """conv2d / conv_transpose2d forward + all gradients against torch on odd shapes."""
+    g = torch.Generator().manual_seed(0)
+    cases = [  # B, Ci, H, W, Co, k, s, p, act, bias, res
+        (2, 3, 13, 17, 8, 7, 2, 3, 'relu', True, False),
+        (2, 15, 12, 20, 16, 5, 2, 2, 'relu', True, False),
+        (1, 17, 9, 11, 16, 3, 1, 1, 'relu', False, True),
+        (2, 8, 10, 14, 1, 3, 1, 1, 'sigmoid', True, False),
+        (2, 16, 8, 12, 24, 1, 1, 0, None, True, False),
+        (2, 32, 7, 9, 64, 1, 2, 0, None, False, False),
+        (2, 65, 6, 10, 32, 3, 2, 1, 'leaky', True, False),
+        (1, 4, 16, 16, 70, 3, 1, 1, 'leaky', True, True),
+    ]
+    if big:
+        cases += [(4, 32, 32, 104, 32, 7, 1, 3, 'relu', True, False), (4, 196, 16, 52, 128, 3, 1, 1, 'leaky', True, False),
+                  (4, 512, 2, 7, 512, 3, 1, 1, 'relu', False, True), (4, 16, 64, 208, 1, 3, 1, 1, 'sigmoid', True, False)]
+    for (B, Ci, H, W, Co, k, s, p, act, bias, res) in cases:
+        x = torch.randn(B, Ci, H, W, generator=g).to(device).requires_grad_(True)
+        w = (torch.randn(Co, Ci, k, k, generator=g) * 0.2).to(device).requires_grad_(True)
+        b = torch.randn(Co, generator=g).to(device).requires_grad_(True) if bias else None
+        Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        r = torch.randn(B, Co, Ho, Wo, generator=g).to(device).requires_grad_(True) if res else None
+        y = cnn.conv2d(x, w, b, r, s, p, act, 0.2)
+        z = F.conv2d(x, w, b, s, p)
+        if res:
+            z = z + r
+        z = {'relu': F.relu, 'sigmoid': torch.sigmoid, 'leaky': lambda t: F.leaky_relu(t, 0.2), None: lambda t: t}[act](z)
+        tag = f'conv {Ci}->{Co} k{k} s{s}'
+        assert_close(y, z, TOL, tag)
+        wt = _wts(y.shape, 1, device)
+        ins = [t for t in (x, w, b, r) if t is not None]
+        ga = torch.autograd.grad((y * wt).sum(), ins)
+        gb = torch.autograd.grad((z * wt).sum(), ins)
+        for a_, b_, nm in zip(ga, gb, ('dx', 'dw', 'db/dres', 'dres')):
+            assert_close(a_, b_, TOL, tag + ' ' + nm)
+    tcases = [(2, 16, 5, 7, 8, 3, 2, 1, 1, 'relu'), (2, 24, 4, 6, 12, 4, 2, 1, 0, 'relu'), (1, 8, 3, 3, 5, 3, 1, 1, 0, None)]
+    if big:
+        tcases += [(4, 512, 2, 7, 512, 3, 2, 1, 1, 'relu'), (4, 96, 32, 104, 32, 4, 2, 1, 0, 'relu')]
+    for (B, Ci, H, W, Co, k, s, p, op, act) in tcases:
+        x = torch.randn(B, Ci, H, W, generator=g).to(device).requires_grad_(True)
+        w = (torch.randn(Ci, Co, k, k, generator=g) * 0.2).to(device).requires_grad_(True)
+        b = torch.randn(Co, generator=g).to(device).requires_grad_(True)
+        y = cnn.conv_transpose2d(x, w, b, s, p, op, act)
+        z = F.conv_transpose2d(x, w, b, s, p, op)
+        z = F.relu(z) if act == 'relu' else z
+        tag = f'convT {Ci}->{Co} k{k} s{s}'
+        assert_close(y, z, TOL, tag)
+        wt = _wts(y.shape, 2, device)
+        ga = torch.autograd.grad((y * wt).sum(), [x, w, b])
+        gb = torch.autograd.grad((z * wt).sum(), [x, w, b])
+        for a_, b_, nm in zip(ga, gb, ('dx', 'dw', 'db')):
+            assert_close(a_, b_, TOL, tag + ' ' + nm)
+
+
+def case_bn_upsample(device):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 6, 5, 7, generator=g).to(device).requires_grad_(True)
+    bn = cnn.BatchNorm2d(6).to(device)
+    ref = torch.nn.BatchNorm2d(6).to(device)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(6, generator=g) + 0.5); bn.bias.copy_(torch.randn(6, generator=g))
+        ref.weight.copy_(bn.weight); ref.bias.copy_(bn.bias)
+    y, z = bn(x), ref(x)
+    assert_close(y, z, TOL, 'bn fwd')
+    wt = _wts(y.shape, 3, device)
+    ga = torch.autograd.grad((y * wt).sum(), [x, bn.weight, bn.bias])
+    gb = torch.autograd.grad((z * wt).sum(), [x, ref.weight, ref.bias])
+    for a_, b_, nm in zip(ga, gb, ('dx', 'dgamma', 'dbeta')):
+        assert_close(a_, b_, TOL, 'bn ' + nm)
+    assert_close(bn.running_mean, ref.running_mean, TOL, 'bn running_mean')
+    assert_close(bn.running_var, ref.running_var, TOL, 'bn running_var')
+    bn.eval(); ref.eval()
+    assert_close(bn(x), ref(x), TOL, 'bn eval')
+    x2 = torch.randn(2, 3, 5, 9, generator=g).to(device).requires_grad_(True)
+    u = cnn.upsample2x(x2)
+    v = F.interpolate(x2, scale_factor=2, mode='bilinear', align_corners=False)
+    assert_close(u, v, 1e-6, 'upsample2x')
+    wt = _wts(u.shape, 4, device)
+    assert_close(torch.autograd.grad((u * wt).sum(), [x2])[0], torch.autograd.grad((v * wt).sum(), [x2])[0], 1e-6, 'upsample2x bwd')
+
+
+def _load(mod, params, device):
+    mod.load_state_dict({k: v.clone() for k, v in params.items()}, strict=True)
+    return mod.to(device)
+
+
+def _check_grads(g, prefix, names, pd, grads, tol):
+    for n, gg in zip(names, grads):
+        k, stride = key_with_stride(g, prefix + n)
+        assert_close(pick(gg, stride), g[k], tol, k)
+
+
+def case_disp_pose_golden(device):
+    """DispResNet6 + PoseNetB6 modules (reference state_dict keys) vs fixtures from the reference nets."""
+    g = golden('nets_small')
+    tgt, refs = synth.frames(2, 64, 128, seed=40)
+    tgt, refs = tgt.to(device), [r.to(device) for r in refs]
+    net = _load(CM.DispResNet6(), ON.disp_params(), device)
+    net.train()
+    disps = net(tgt)
+    for i, x in enumerate(disps):
+        assert_close(x, g[f'disp_out{i}'], TOL, f'disp{i}')
+    names = ['conv1.0.weight', 'conv1.2.bias', 'conv2.0.conv1.weight', 'conv2.0.downsample.0.weight',
+             'conv2.0.downsample.1.weight', 'conv2.0.downsample.1.bias', 'conv7.1.conv2.weight',
+             'upconv7.0.weight', 'upconv1.0.bias', 'iconv1.0.conv1.weight', 'iconv3.0.downsample.0.weight',
+             'predict_disp1.0.weight', 'predict_disp6.0.bias']
+    pd = dict(net.named_parameters())
+    loss = sum((x * _wts(x.shape, 50 + i, device)).sum() for i, x in enumerate(disps))
+    _check_grads(g, 'disp_g_', names, pd, torch.autograd.grad(loss, [pd[n] for n in names]), 5e-4)
+    sd = net.state_dict()
+    assert_close(sd['conv2.0.downsample.1.running_mean'], g['disp_rm'], TOL, 'running_mean')
+    assert_close(sd['iconv1.0.downsample.1.running_var'], g['disp_rv'], TOL, 'running_var')
+    net.eval()
+    with torch.no_grad():
+        assert_close(net(tgt), g['disp_eval'], TOL, 'disp eval')
+        net.train()
+        t2, _ = synth.frames(2, 40, 104, seed=41)
+        for i, x in enumerate(net(t2.to(device))):
+            assert_close(x, g[f'disp_odd_out{i}'], TOL, f'disp odd {i}')
+    pnet = _load(CM.PoseNetB6(nb_ref_imgs=4), ON.pose_params(), device)
+    pose = pnet(tgt, refs)
+    assert_close(pose, g['pose_out'], TOL, 'pose')
+    pn = ['conv1.0.weight', 'conv2.0.weight', 'conv8.0.bias', 'pose_pred.weight', 'pose_pred.bias']
+    ppd = dict(pnet.named_parameters())
+    _check_grads(g, 'pose_g_', pn, ppd, torch.autograd.grad((pose * _wts(pose.shape, 60, device)).sum(), [ppd[n] for n in pn]), 5e-4)
+
+
+def case_mask_golden(device):
+    g = golden('nets_small')
+    tgt, refs = synth.frames(2, 64, 128, seed=40)
+    tgt, refs = tgt.to(device), [r.to(device) for r in refs]
+    mnet = _load(CM.MaskNet6(nb_ref_imgs=4, output_exp=True), ON.mask_params(), device)
+    mnet.train()
+    ms = mnet(tgt, refs)
+    for i, x in enumerate(ms):
+        assert_close(x, g[f'mask_out{i}'], TOL, f'mask{i}')
+    mn = ['conv1.0.weight', 'conv6.0.weight', 'deconv6.0.weight', 'deconv1.0.weight', 'deconv3.0.bias',
+          'pred_mask1.weight', 'pred_mask6.bias']
+    mpd = dict(mnet.named_parameters())
+    loss = sum((x * _wts(x.shape, 70 + i, device)).sum() for i, x in enumerate(ms))
+    _check_grads(g, 'mask_g_', mn, mpd, torch.autograd.grad(loss, [mpd[n] for n in mn]), 5e-4)
+
+
+def smoke_case(device):
+    case_conv_shapes(device)
+
+
+NET_CASES = [case_conv_shapes, case_bn_upsample, case_disp_pose_golden, case_mask_golden]

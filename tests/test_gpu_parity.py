@@ -55,3 +55,16 @@ def test_full_size_properties():
     g2 = torch.autograd.grad((2.5 * o).sum(), [depth, pose])
     for a, b in zip(g1, g2):
         assert (2.5 * a - b).abs().max().item() <= 1e-5 * b.abs().max().item() + 1e-12
+
+
+from tests import net_cases as NC   # noqa: E402
+
+
+@pytest.mark.parametrize('case', NC.NET_CASES, ids=lambda f: f.__name__)
+def test_net_case(case):
+    case(torch.device('cuda:0'))
+    torch.cuda.synchronize()
+
+
+def test_conv_big_shapes():
+    NC.case_conv_shapes(torch.device('cuda:0'), big=True)

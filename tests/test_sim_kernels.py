@@ -29,3 +29,11 @@ from tests import kernel_cases as KC   # noqa: E402
 @pytest.mark.parametrize('case', KC.ALL_CASES, ids=lambda f: f.__name__)
 def test_case(case):
     case(torch.device('cpu'))
+
+
+from tests import net_cases as NC   # noqa: E402
+
+
+@pytest.mark.parametrize('case', NC.NET_CASES, ids=lambda f: f.__name__)
+def test_net_case(case):
+    case(torch.device('cpu'))

@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the Competitive-Collaboration training step on B200.
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference ...                    (the reference algorithm's CPU path: oracle port)
+
+One JSON line on rank 0.  metric = BASELINE.json's "train-step triplets/sec at 256x832x6lvl": frame
+snippets (target + 4 references) per second through forward + losses + backward + Adam.
+
+  value     device-resident inputs, whole step replayed as one CUDA graph, CUDA-event timed, max over ranks
+  e2e       same step through the public API with HOST (pinned) inputs: H2D of the 5 frames + intrinsics and
+            a D2H read of the loss inside the timed region, every step
+  roofline  dominant kernel family (by measured share of the step) against the measured B200 peak;
+            roofline_warploss is the fused warp+loss kernel against the HBM peak (BASELINE metric, 2nd half)
+  cpu_baseline  the oracle port of the reference step on this box's host cores (bounded sample)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H, W, NLEVELS = 256, 832, 6
+PER_GPU_BATCH = 4
+CFG_WORKLOAD = {
+    'cfg1': 'cfg1: DispResNet6+PoseNetB6 depth/pose step, 256x832 b4/GPU, 6 pyramid levels '
+            '(photometric_reconstruction_loss + edge-aware smoothness, fwd+bwd+Adam)',
+    'cfg3': 'cfg3: full CC joint step (Disp+Pose+Mask+Flow, 5 losses), 256x832 b4/GPU, 6 levels, fwd+bwd+Adam',
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tensor_burst=d['bf16_tflops'], tensor_sustained=d['bf16_tflops_sustained'],
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                if v.strip().lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), samples=len(sm), reasons=sorted(reasons))
+
+
+# ---------------------------------------------------------------------------------------------------
+def host_batches(nb, B, seed0):
+    """nb synthetic batches of the reference's sample contract in PINNED host memory."""
+    from cc_b200 import synth
+    out = []
+    for i in range(nb):
+        tgt, refs = synth.frames(B, H, W, seed=seed0 + i)
+        K, Kinv = synth.intrinsics(B, H, W)
+        ts = [tgt] + refs + [K, Kinv]
+        if torch.cuda.is_available():
+            ts = [t.pin_memory() for t in ts]
+        out.append(ts)
+    return out
+
+
+def run_ours(args):
+    from cc_b200 import _lib, dist as cdist, pyramid
+    from cc_b200.train_step import Trainer
+    rank, local, world = cdist.init_from_env()
+    assert world == args.gpus, 'WORLD_SIZE %d != --gpus %d (launch with torch.distributed.run)' % (world, args.gpus)
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    B = PER_GPU_BATCH
+    trainer = Trainer(args.cfg, dev, seed=0)
+    hb = host_batches(4, B, seed0=1000 * rank)
+    static = [torch.empty_like(t, device=dev) for t in hb[0]]
+    for s, h in zip(static, hb[0]):
+        s.copy_(h)
+    tgt, refs, K, Kinv = static[0], static[1:5], static[5], static[6]
+    in_bytes = sum(t.numel() * 4 for t in hb[0])
+
+    # one eager step to count our launches per step, then capture the step as a CUDA graph
+    torch.cuda.synchronize()
+    pyramid.clear()
+    trainer.step(tgt, refs, K, Kinv)
+    c0 = _lib.lib().ccb_launch_count()
+    pyramid.clear()
+    trainer.step(tgt, refs, K, Kinv)
+    launches_per_step = _lib.lib().ccb_launch_count() - c0
+    use_graph = not args.no_graph
+    if use_graph:
+        trainer.capture(tgt, refs, K, Kinv, warmup=1)
+
+    def one_step():
+        if use_graph:
+            return trainer.replay()
+        pyramid.clear()
+        return trainer.step(tgt, refs, K, Kinv)[0]
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    # ---- value: device-resident inputs --------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    torch.cuda.synchronize(); cdist.barrier()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = one_step()
+    e1.record()
+    torch.cuda.synchronize(); cdist.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = cdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    # ---- e2e: host inputs, H2D + D2H inside the timed region ----------------------------------------
+    loss_host = torch.empty(1).pin_memory()
+    for i in range(2):
+        for s, h in zip(static, hb[i % len(hb)]):
+            s.copy_(h, non_blocking=True)
+        one_step()
+    torch.cuda.synchronize(); cdist.barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        for s, h in zip(static, hb[i % len(hb)]):
+            s.copy_(h, non_blocking=True)
+        loss = one_step()
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the reference reads loss.item() every step
+    f1.record()
+    torch.cuda.synchronize(); cdist.barrier()
+    ms_e2e = cdist.max_over_ranks(f0.elapsed_time(f1), dev)
+    last_loss = float(loss_host[0])
+
+    out = None
+    if rank == 0:
+        pk = peaks()
+        prof = profile_pass(trainer, tgt, refs, K, Kinv) if not args.no_profile else {}
+        value = world * B * args.steps / (ms_total * 1e-3)
+        e2e = world * B * args.steps / (ms_e2e * 1e-3)
+        out = {
+            'metric': 'train-step triplets/sec at 256x832x6lvl', 'value': value, 'unit': 'triplets/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': CFG_WORKLOAD[args.cfg], 'global_batch': world * B, 'per_gpu_batch': B,
+                       'frame': '%dx%d' % (H, W), 'levels': NLEVELS, 'parallelism': 'dp%d' % world,
+                       'conv_math': prof.get('conv_math', 'fp32'), 'cuda_graph': use_graph,
+                       'l2_policy': 'inputs and activations (~1 GB/step) exceed the 126 MB L2; no explicit flush'},
+            'e2e': {'value': e2e, 'unit': 'triplets/s', 'h2d_bytes_per_step': in_bytes, 'd2h_bytes_per_step': 4,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': int(launches_per_step * args.steps), 'gpu_launches_per_step': int(launches_per_step),
+            'clocks': clocks, 'loss': last_loss, 'peaks': pk,
+        }
+        out.update(prof.get('json', {}))
+        if world == 1 and not args.no_cpu_baseline:
+            out['cpu_baseline'] = cpu_baseline(args.cfg, budget_s=25.0)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+def profile_pass(trainer, tgt, refs, K, Kinv, steps=2):
+    """Per-entry-point CUDA-event timing of the step (eager, on the launching stream) -> kernel shares,
+    and the roofline objects for the dominant family and for the fused warp+loss kernels."""
+    from cc_b200 import _lib, pyramid
+    pk = peaks()
+    records = []
+    real = _lib.lib()
+
+    class Proxy:
+        def __getattr__(self, name):
+            fn = getattr(real, name)
+            if not name.startswith('ccb_') or name.endswith('_floats') or name in ('ccb_launch_count', 'ccb_last_error_string'):
+                return fn
+
+            def wrapped(*a):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                rc = fn(*a)
+                e.record()
+                records.append((name, a[0], s, e))
+                return rc
+            return wrapped
+
+    saved = _lib._lib
+    for it in range(steps + 1):
+        if it == 1:
+            records.clear()
+        _lib._lib = Proxy()
+        try:
+            pyramid.clear()
+            trainer.step(tgt, refs, K, Kinv)
+        finally:
+            _lib._lib = saved
+        torch.cuda.synchronize()
+    fam = {}
+    for name, a0, s, e in records:
+        ms = s.elapsed_time(e)
+        f = fam.setdefault(name, dict(ms=0.0, calls=0, flops=0.0, bytes=0.0))
+        f['ms'] += ms
+        f['calls'] += 1
+        if name.startswith('ccb_conv2d_'):
+            d = a0._obj if hasattr(a0, '_obj') else a0
+            f['flops'] += 2.0 * d.B * d.Co * d.Ho * d.Wo * d.Ci * d.kh * d.kw
+        elif name.startswith('ccb_photo_loss_'):
+            d = a0._obj if hasattr(a0, '_obj') else a0
+            px = sum(d.B * d.h[l] * d.w[l] for l in range(d.nlevels))
+            # rigid 80 B/px fwd (+20 bwd) with mask; 64 (+4) without; flow 60 (+24)
+            if d.mode == 0:
+                per = (80 if d.has_mask else 64) if name.endswith('fwd') else (20 if d.has_mask else 4)
+            else:
+                per = (60 if d.has_mask else 52) if name.endswith('fwd') else (24 if d.has_mask else 16)
+            f['bytes'] += float(px) * per
+    total = sum(f['ms'] for f in fam.values())
+    conv = {k: v for k, v in fam.items() if k.startswith('ccb_conv2d_')}
+    conv_ms = sum(v['ms'] for v in conv.values())
+    conv_flops = sum(v['flops'] for v in conv.values())
+    photo = {k: v for k, v in fam.items() if k.startswith('ccb_photo_loss_')}
+    photo_ms = sum(v['ms'] for v in photo.values())
+    photo_bytes = sum(v['bytes'] for v in photo.values())
+    js = {}
+    if conv_ms > 0:
+        ach = conv_flops / (conv_ms * 1e-3) / 1e12
+        js['roofline'] = {'bound': 'tensor', 'kernel': 'conv2d fprop+dgrad+wgrad (implicit GEMM)', 'achieved': ach,
+                          'peak': pk['tensor_sustained'], 'unit': 'TFLOP/s', 'frac': ach / pk['tensor_sustained'],
+                          'traffic': None, 'share_of_step': conv_ms / total, 'launches': sum(v['calls'] for v in conv.values()) // steps,
+                          'peak_source': pk['source'] + ' bf16 sustained; convs accumulate in fp32 (see DESIGN.md)'}
+    if photo_ms > 0:
+        ach = photo_bytes / (photo_ms * 1e-3) / 1e9
+        js['roofline_warploss'] = {'bound': 'hbm', 'kernel': 'photo_fwd+photo_bwd (fused warp+SSIM+loss)', 'achieved': ach,
+                                   'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'], 'traffic': None,
+                                   'share_of_step': photo_ms / total, 'peak_source': pk['source']}
+    js['kernel_shares'] = {k: round(v['ms'] / total, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]['ms'])[:8]}
+    js['profiled_step_ms'] = total / steps
+    return {'json': js}
+
+
+# ---------------------------------------------------------------------------------------------------
+def _oracle_step_timer(cfg, B, threads):
+    from cc_b200 import synth
+    from oracle import step as OS
+    torch.set_num_threads(threads)
+    P = OS.make_params(cfg)
+    opt = OS.Adam(OS.all_params(P), OS.HP['lr'], OS.HP['beta1'], OS.HP['beta2'])
+    tgt, refs = synth.frames(B, H, W, seed=7)
+    K, Kinv = synth.intrinsics(B, H, W)
+
+    def run():
+        t0 = time.perf_counter()
+        OS.train_step(cfg, P, opt, tgt, refs, K, Kinv)
+        return time.perf_counter() - t0
+    return run
+
+
+def cpu_baseline(cfg, budget_s=25.0):
+    """The oracle port of the reference step on the host cores, bounded to ~budget_s of CPU work."""
+    threads = os.cpu_count() or 1
+    B = 2
+    run = _oracle_step_timer(cfg, B, threads)
+    t_first = run()                      # warm-up (allocator, thread pool)
+    ts = [run()]
+    while sum(ts) + t_first + ts[-1] < budget_s and len(ts) < 5:
+        ts.append(run())
+    ts.sort()
+    t = ts[len(ts) // 2]
+    return {'value': B / t, 'unit': 'triplets/s', 'cores': threads, 'kind': 'port',
+            'sample': '%s oracle step (fwd+bwd+Adam) at b%d 256x832x6lvl, torch CPU fp32, median of %d after 1 warm-up' % (cfg, B, len(ts)),
+            's_per_step': t}
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's own CPU path (oracle port; the reference is pure Python/
+    PyTorch and cannot travel to the GPU box), all host threads, rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return None
+    threads = os.cpu_count() or 1
+    B = 2
+    run = _oracle_step_timer(args.cfg, B, threads)
+    probe = run()
+    if probe * (args.steps + args.warmup) > 280 and B > 1:     # keep the whole run within a few minutes
+        B = 1
+        run = _oracle_step_timer(args.cfg, B, threads)
+        run()
+    for _ in range(max(0, args.warmup - 1)):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = time.perf_counter() - t0
+    v = B * args.steps / dt
+    return {'impl': 'reference', 'metric': 'train-step triplets/sec at 256x832x6lvl', 'value': v, 'unit': 'triplets/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': CFG_WORKLOAD[args.cfg], 'sample_batch_per_step': B, 'frame': '%dx%d' % (H, W),
+                       'levels': NLEVELS, 'device': 'host CPU'},
+            'cpu_baseline': {'value': v, 'unit': 'triplets/s', 'cores': threads, 'kind': 'port',
+                             'sample': 'oracle %s step at b%d per step, %d steps' % (args.cfg, B, args.steps)},
+            'e2e': {'value': v, 'unit': 'triplets/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cfg', default='cfg1', choices=sorted(CFG_WORKLOAD))
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    out = run_reference(args) if args.impl == 'reference' else run_ours(args)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()

@@ -108,7 +108,8 @@ _SIGS = {
     'ccb_bn_bwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     'ccb_upsample2x_fwd': (_I, [_P, _P, _I, _I, _I, _P]),
     'ccb_upsample2x_bwd': (_I, [_P, _P, _I, _I, _I, _P]),
-    'ccb_adam_step': (_I, [_P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _F, _P]),
+    'ccb_adam_step': (_I, [_P, _P, _P, _P, _LL, _P, _F, _F, _F, _F, _F, _P]),
+    'ccb_launch_count': (_LL, []),
 }
 # entry points added by later translation units register themselves here (conv, nets, optimiser ...)
 EXTRA_SIGS = {}

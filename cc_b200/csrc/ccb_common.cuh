@@ -10,10 +10,17 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
-#define CCB_LAUNCH(kern, grid, block, smem, stream, ...) \
-    kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define CCB_LAUNCH(kern, grid, block, smem, stream, ...)                           \
+    do {                                                                            \
+        ++ccb::g_launches;                                                          \
+        kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);     \
+    } while (0)
 #define CCB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
+
+namespace ccb {
+extern long long g_launches;   // kernels launched through the library by this process (bench.py gpu_launches)
+}
 
 namespace ccb {
 

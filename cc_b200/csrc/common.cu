@@ -5,6 +5,7 @@
 namespace ccb {
 
 static thread_local char g_err[512] = "";
+long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -26,6 +27,7 @@ int check_launch(const char* what) {
 
 extern "C" const char* ccb_last_error_string(void) { return ccb::g_err; }
 extern "C" int ccb_version(void) { return 100; }
+extern "C" long long ccb_launch_count(void) { return ccb::g_launches; }
 extern "C" int ccb_is_simulator(void) {
 #ifdef CCB_CPU_SIM
     return 1;

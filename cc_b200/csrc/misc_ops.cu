@@ -158,12 +158,24 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const float* __rest
 }
 
 // ---- Adam over a flat parameter / gradient buffer (torch.optim.Adam semantics, no weight decay) ----
+// The step counter and bias corrections live in device memory (state[0..2] = step, 1-b1^t, sqrt(1-b2^t))
+// so that the whole training step can be captured once in a CUDA graph and replayed.
+__global__ void adam_prep_kernel(float* __restrict__ state, float b1, float b2) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float t = state[0] + 1.f;
+        state[0] = t;
+        state[1] = (float)(1.0 - pow((double)b1, (double)t));
+        state[2] = (float)sqrt(1.0 - pow((double)b2, (double)t));
+    }
+}
+
 // grad_scale multiplies the gradient first (1/world_size after the NCCL sum).
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                   float* __restrict__ v, long long n, float lr, float b1, float b2,
-                                                   float eps, float bc1, float bc2_sqrt, float grad_scale) {
+                                                   float* __restrict__ v, long long n, const float* __restrict__ state,
+                                                   float lr, float b1, float b2, float eps, float grad_scale) {
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
+    const float bc1 = __ldg(state + 1), bc2_sqrt = __ldg(state + 2);
     float gi = __ldg(g + i) * grad_scale;
     float mi = b1 * m[i] + (1.f - b1) * gi;
     float vi = b2 * v[i] + (1.f - b2) * gi * gi;
@@ -214,13 +226,14 @@ extern "C" int ccb_upsample2x_bwd(const float* dy, float* dx, int planes, int h,
     return check_launch("upsample2x_bwd");
 }
 
-extern "C" int ccb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step,
-                             float lr, float beta1, float beta2, float eps, float grad_scale, ccb_stream_t stream) {
-    CCB_REQUIRE(params && grads && exp_avg && exp_avg_sq && n >= 0 && step >= 1, CCB_ERR_ARG, "adam_step: bad argument");
-    if (n == 0) return CCB_OK;
-    double bc1 = 1.0 - pow((double)beta1, (double)step);
-    double bc2 = 1.0 - pow((double)beta2, (double)step);
-    CCB_LAUNCH(adam_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, params, grads, exp_avg, exp_avg_sq, n, lr,
-               beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+extern "C" int ccb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                             float* state, float lr, float beta1, float beta2, float eps, float grad_scale,
+                             ccb_stream_t stream) {
+    CCB_REQUIRE(params && grads && exp_avg && exp_avg_sq && state && n >= 0, CCB_ERR_ARG, "adam_step: bad argument");
+    CCB_LAUNCH(adam_prep_kernel, dim3(1), dim3(32), 0, stream, state, beta1, beta2);
+    int rc = check_launch("adam_prep");
+    if (rc || n == 0) return rc;
+    CCB_LAUNCH(adam_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, params, grads, exp_avg, exp_avg_sq, n,
+               (const float*)state, lr, beta1, beta2, eps, grad_scale);
     return check_launch("adam_step");
 }

@@ -469,7 +469,7 @@ template <int MODE, bool SSIM>
 static int launch_fwd(const PhotoArgs& a, cudaStream_t st) {
     auto k = photo_fwd_kernel<MODE, SSIM>;
     size_t sm = SSIM ? fwd_smem<6>() : fwd_smem<0>();
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    { static bool once = false; if (!once) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); once = true; } }
     CCB_LAUNCH(k, dim3(a.blk_off[a.d.nlevels]), dim3(NT), sm, st, a);
     return check_launch("photo_fwd");
 }
@@ -477,7 +477,7 @@ template <int MODE, bool SSIM>
 static int launch_bwd(const PhotoArgs& a, cudaStream_t st) {
     auto k = photo_bwd_kernel<MODE, SSIM>;
     size_t sm = bwd_smem();
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    { static bool once = false; if (!once) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); once = true; } }
     CCB_LAUNCH(k, dim3(a.blk_off[a.d.nlevels]), dim3(NT), sm, st, a);
     return check_launch("photo_bwd");
 }

@@ -298,7 +298,7 @@ static int smooth_args(const ccb_smooth_desc* d, SmoothArgs& a, bool bwd) {
         wgt /= 2.3;
     }
     for (int l = 0; l < d->nlevels; ++l) {
-        CCB_REQUIRE(d->h[l] >= 3 && d->w[l] >= 3, CCB_ERR_ARG, "smooth: level %d size %dx%d < 3", l, d->h[l], d->w[l]);
+        CCB_REQUIRE(d->h[l] >= 1 && d->w[l] >= 1, CCB_ERR_ARG, "smooth: level %d size %dx%d", l, d->h[l], d->w[l]);
         CCB_REQUIRE(d->pred[l] != nullptr, CCB_ERR_ARG, "smooth: pred[%d] null", l);
         if (d->kind == CCB_SMOOTH_EDGE) CCB_REQUIRE(d->img[l] != nullptr, CCB_ERR_ARG, "smooth: img[%d] null", l);
         if (bwd) CCB_REQUIRE(d->d_pred[l] != nullptr, CCB_ERR_ARG, "smooth: d_pred[%d] null", l);

@@ -456,7 +456,7 @@ extern "C" int ccb_ssim_fwd(const float* img1, const float* img2, int planes, in
     a.x = img1; a.y = img2; a.out = out; a.planes = planes; a.h = h; a.w = w;
     for (int k = 0; k < CCB_SSIM_TAPS; ++k) a.taps[k] = taps_host[k];
     auto kfn = ssim_map_kernel<0>;
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssim_smem_fwd());
+    { static bool once = false; if (!once) { cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssim_smem_fwd()); once = true; } }
     CCB_LAUNCH(kfn, dim3(cdiv(w, TW), cdiv(h, TH), planes), dim3(NT), ssim_smem_fwd(), stream, a);
     return check_launch("ssim_fwd");
 }
@@ -470,12 +470,12 @@ extern "C" int ccb_ssim_bwd(const float* img1, const float* img2, int planes, in
     a.planes = planes; a.h = h; a.w = w;
     for (int k = 0; k < CCB_SSIM_TAPS; ++k) a.taps[k] = taps_host[k];
     auto k1 = ssim_map_kernel<1>;
-    cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssim_smem_fwd());
+    { static bool once = false; if (!once) { cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssim_smem_fwd()); once = true; } }
     CCB_LAUNCH(k1, dim3(cdiv(w, TW), cdiv(h, TH), planes), dim3(NT), ssim_smem_fwd(), stream, a);
     int rc = check_launch("ssim_bwd_maps");
     if (rc) return rc;
     auto k2 = ssim_bwd_kernel;
-    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssim_smem_bwd());
+    { static bool once = false; if (!once) { cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssim_smem_bwd()); once = true; } }
     CCB_LAUNCH(k2, dim3(cdiv(w, TW), cdiv(h, TH), planes), dim3(NT), ssim_smem_bwd(), stream, a);
     return check_launch("ssim_bwd");
 }

@@ -49,6 +49,17 @@ def _run(op, d, *args):
     _lib.check(fn(C.byref(d), *ptrs, _lib.ptr(work), wf, _lib.stream(args[0])), 'conv op %d' % op)
 
 
+def _grad_slot(param, like):
+    """Where a parameter gradient is written: straight into the optimiser's flat gradient buffer when
+    the parameter is registered with cc_b200.optim.FlatAdam (no AccumulateGrad add), else a new tensor.
+    Returns (tensor, direct)."""
+    slot = getattr(param, '_ccb_grad', None) if param is not None else None
+    if slot is not None and not param._ccb_written:
+        param._ccb_written = True
+        return slot, True
+    return torch.empty_like(like), False
+
+
 def _act_bwd(g, y, act, slope):
     if act == _lib.ACT_NONE:
         return g
@@ -63,6 +74,7 @@ class _Conv2dFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, bias, res, stride, pad, act, slope):
+        w_in, b_in = w, bias
         x, w = _c(x), _c(w)
         bias = _c(bias) if bias is not None else None
         res = _c(res) if res is not None else None
@@ -74,6 +86,7 @@ class _Conv2dFn(torch.autograd.Function):
         _run(_lib.CONV_FPROP, d, x, w, bias, res, y)
         ctx.save_for_backward(x, w, y if act != _lib.ACT_NONE else None)
         ctx.cfg = (stride, pad, act, slope, bias is not None, res is not None)
+        ctx.params = (w_in, b_in)
         return y
 
     @staticmethod
@@ -89,9 +102,11 @@ class _Conv2dFn(torch.autograd.Function):
             dx = torch.empty_like(x)
             _run(_lib.CONV_DGRAD, d, dz, w, None, None, dx)
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
-            dw = torch.empty_like(w)
-            db = torch.empty(Co, device=x.device) if has_bias else None
+            dw, w_direct = _grad_slot(ctx.params[0], w)
+            db, b_direct = _grad_slot(ctx.params[1], w.new_empty(Co)) if has_bias else (None, False)
             _run(_lib.CONV_WGRAD, d, x, dz, dw, db)
+            dw = None if w_direct else dw
+            db = None if b_direct else db
         return dx, dw, db, (dz if has_res else None), None, None, None, None
 
 
@@ -101,6 +116,7 @@ class _ConvT2dFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, bias, stride, pad, out_pad, act, slope):
+        w_in, b_in = w, bias
         x, w = _c(x), _c(w)
         bias = _c(bias) if bias is not None else None
         B, Cin, h, wd = x.shape
@@ -112,6 +128,7 @@ class _ConvT2dFn(torch.autograd.Function):
         _run(_lib.CONV_DGRAD, d, x, w, bias, None, y)
         ctx.save_for_backward(x, w, y if act != _lib.ACT_NONE else None)
         ctx.cfg = (stride, pad, act, slope, bias is not None, H, W)
+        ctx.params = (w_in, b_in)
         return y
 
     @staticmethod
@@ -127,17 +144,20 @@ class _ConvT2dFn(torch.autograd.Function):
             dx = torch.empty_like(x)
             _run(_lib.CONV_FPROP, d, dz, w, None, None, dx)
         if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(w)
+            dw, direct = _grad_slot(ctx.params[0], w)
             _run(_lib.CONV_WGRAD, d, dz, x, dw, None)        # roles swapped: activations = dz, grads = x
+            dw = None if direct else dw
         if has_bias and ctx.needs_input_grad[2]:
-            db = torch.empty(Cout, device=x.device)
+            db, direct = _grad_slot(ctx.params[1], w.new_empty(Cout))
             _lib.check(_lib.lib().ccb_bias_grad(_lib.ptr(dz), _lib.ptr(db), B, Cout, H * W, _lib.stream(dz)), 'bias_grad')
+            db = None if direct else db
         return dx, dw, db, None, None, None, None, None
 
 
 class _BatchNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, rm, rv, training, eps, momentum):
+        ctx.params = (gamma, beta)
         x, gamma, beta = _c(x), _c(gamma), _c(beta)
         B, Cc, h, w = x.shape
         y = torch.empty_like(x)
@@ -156,10 +176,12 @@ class _BatchNormFn(torch.autograd.Function):
             raise NotImplementedError('cc_b200: BatchNorm backward is implemented for training mode only')
         B, Cc, h, w = x.shape
         g = _c(g)
-        dx, dg, db = torch.empty_like(x), torch.empty_like(gamma), torch.empty_like(gamma)
+        dx = torch.empty_like(x)
+        dg, g_direct = _grad_slot(ctx.params[0], gamma)
+        db, b_direct = _grad_slot(ctx.params[1], gamma)
         _lib.check(_lib.lib().ccb_bn_bwd(_lib.ptr(x), _lib.ptr(g), _lib.ptr(gamma), _lib.ptr(stats), _lib.ptr(dx),
                                          _lib.ptr(dg), _lib.ptr(db), B, Cc, h * w, _lib.stream(x)), 'bn_bwd')
-        return dx, dg, db, None, None, None, None, None
+        return dx, (None if g_direct else dg), (None if b_direct else db), None, None, None, None, None
 
 
 class _Upsample2xFn(torch.autograd.Function):

@@ -236,9 +236,14 @@ int ccb_bn_bwd(const float* x, const float* dy, const float* gamma, const float*
 int ccb_upsample2x_fwd(const float* x, float* y, int planes, int h, int w, ccb_stream_t stream);
 int ccb_upsample2x_bwd(const float* dy, float* dx, int planes, int h, int w, ccb_stream_t stream);
 /* torch.optim.Adam step (train.py:307-310,568) on one flat fp32 buffer; grad_scale pre-multiplies the
- * gradient (1/world_size after the NCCL all-reduce sum).  `step` is the 1-based step count. */
-int ccb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step,
-                  float lr, float beta1, float beta2, float eps, float grad_scale, ccb_stream_t stream);
+ * gradient (1/world_size after the NCCL all-reduce sum).  state: 3 device floats {step count, 1-b1^t,
+ * sqrt(1-b2^t)}, zero-initialised by the caller; the call increments the step on the device, so a
+ * captured CUDA graph of the training step replays correctly. */
+int ccb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                  float* state, float lr, float beta1, float beta2, float eps, float grad_scale,
+                  ccb_stream_t stream);
+/* number of kernel launches issued through this library by the calling process so far */
+long long ccb_launch_count(void);
 
 #ifdef __cplusplus
 }

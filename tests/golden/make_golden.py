@@ -211,7 +211,7 @@ def load_ref(mod, params):
 
 def gen_nets():
     d = {}
-    B, H, W = 2, 64, 128
+    B, H, W = 2, 32, 64          # DispResNet6 / PoseNetB6 (any size works: crop_like)
     tgt, refs = synth.frames(B, H, W, seed=40)
     # DispResNet6
     P = onets.disp_params()
@@ -237,7 +237,7 @@ def gen_nets():
     net.eval()
     d['disp_eval'] = net(tgt)
     # odd size: crop_like path (128x416-like aspect: 40x104)
-    t2, _ = synth.frames(2, 40, 104, seed=41)
+    t2, _ = synth.frames(2, 24, 40, seed=41)
     net.train()
     o2 = net(t2)
     for i, x in enumerate(o2):
@@ -254,7 +254,9 @@ def gen_nets():
     for n, gg in zip(pn, g):
         sfx, gg = compact(gg)
         d['pose_g_' + n + sfx] = gg
-    # MaskNet6
+    # MaskNet6 / Back2Future need H, W divisible by 64
+    B, H, W = 1, 64, 64
+    tgt, refs = synth.frames(B, H, W, seed=42)
     Pm = onets.mask_params()
     mnet = load_ref(RM.MaskNet6(nb_ref_imgs=4, output_exp=True), Pm)
     mnet.train()

@@ -108,7 +108,7 @@ def _check_grads(g, prefix, names, pd, grads, tol):
 def case_disp_pose_golden(device):
     """DispResNet6 + PoseNetB6 modules (reference state_dict keys) vs fixtures from the reference nets."""
     g = golden('nets_small')
-    tgt, refs = synth.frames(2, 64, 128, seed=40)
+    tgt, refs = synth.frames(2, 32, 64, seed=40)
     tgt, refs = tgt.to(device), [r.to(device) for r in refs]
     net = _load(CM.DispResNet6(), ON.disp_params(), device)
     net.train()
@@ -129,7 +129,7 @@ def case_disp_pose_golden(device):
     with torch.no_grad():
         assert_close(net(tgt), g['disp_eval'], TOL, 'disp eval')
         net.train()
-        t2, _ = synth.frames(2, 40, 104, seed=41)
+        t2, _ = synth.frames(2, 24, 40, seed=41)
         for i, x in enumerate(net(t2.to(device))):
             assert_close(x, g[f'disp_odd_out{i}'], TOL, f'disp odd {i}')
     pnet = _load(CM.PoseNetB6(nb_ref_imgs=4), ON.pose_params(), device)
@@ -142,7 +142,7 @@ def case_disp_pose_golden(device):
 
 def case_mask_golden(device):
     g = golden('nets_small')
-    tgt, refs = synth.frames(2, 64, 128, seed=40)
+    tgt, refs = synth.frames(1, 64, 64, seed=42)
     tgt, refs = tgt.to(device), [r.to(device) for r in refs]
     mnet = _load(CM.MaskNet6(nb_ref_imgs=4, output_exp=True), ON.mask_params(), device)
     mnet.train()

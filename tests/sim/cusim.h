@@ -179,6 +179,10 @@ static inline unsigned atomicInc(unsigned* p, unsigned lim) { unsigned o = *p; *
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 
-#define CCB_LAUNCH(kern, grid, block, smem, stream, ...) \
-    cusim::launch(grid, block, smem, [&]() { kern(__VA_ARGS__); })
+#define CCB_LAUNCH(kern, grid, block, smem, stream, ...)                     \
+    do {                                                                      \
+        ++ccb::g_launches;                                                    \
+        cusim::launch(grid, block, smem, [&]() { kern(__VA_ARGS__); });       \
+    } while (0)
+namespace ccb { extern long long g_launches; }
 #define CCB_DYN_SMEM(name) unsigned char* name = cusim::dyn_smem()

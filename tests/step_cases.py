@@ -1,0 +1,65 @@
+"""Step-level parity: cc_b200.train_step.Trainer (nets + fused losses + flat Adam) vs the oracle's
+train_step (reference train.py:445-568 restated) on identical seeded inputs / weights."""
+import torch
+from tests.util import assert_close
+from cc_b200 import synth, nn as cnn
+from cc_b200.optim import FlatAdam
+from cc_b200.train_step import Trainer, HP
+from oracle import step as OS, nets as ON
+
+
+def case_flat_adam(device):
+    """Two conv layers trained 3 steps: FlatAdam (direct flat-buffer weight grads) vs torch.optim.Adam."""
+    torch.manual_seed(0)
+    c1, c2 = cnn.Conv2d(3, 8, 3, padding=1, act='relu').to(device), cnn.Conv2d(8, 2, 3, padding=1).to(device)
+    r1, r2 = torch.nn.Conv2d(3, 8, 3, padding=1).to(device), torch.nn.Conv2d(8, 2, 3, padding=1).to(device)
+    for a, b in ((c1, r1), (c2, r2)):
+        b.load_state_dict(a.state_dict())
+    x = torch.randn(2, 3, 9, 11, generator=torch.Generator().manual_seed(1)).to(device)
+    opt = FlatAdam(list(c1.parameters()) + list(c2.parameters()), lr=1e-2)
+    ropt = torch.optim.Adam(list(r1.parameters()) + list(r2.parameters()), lr=1e-2)
+    for _ in range(3):
+        opt.zero_grad()
+        l = (c2(c1(x)) ** 2).mean()
+        l.backward()
+        opt.step()
+        ropt.zero_grad()
+        lr_ = (r2(torch.relu(r1(x))) ** 2).mean()
+        lr_.backward()
+        ropt.step()
+        assert_close(l, lr_, 1e-5, 'loss')
+    for a, b in ((c1, r1), (c2, r2)):
+        assert_close(a.weight, b.weight, 1e-4, 'weight after 3 Adam steps')
+        assert_close(a.bias, b.bias, 1e-4, 'bias after 3 Adam steps')
+    assert abs(opt.state[0].item() - 3.0) < 1e-6
+
+
+def _oracle_params_as_state_dicts(P):
+    return {n: {k: v.detach().clone() for k, v in d.items()} for n, d in P.items()}
+
+
+def case_step_cfg1(device, B=2, H=128, W=416, steps=2):
+    """cfg1 (BASELINE.json configs[1] at reduced batch/size): loss and gradients of step 1, loss of step 2."""
+    tgt, refs = synth.frames(B, H, W, seed=50)
+    K, Kinv = synth.intrinsics(B, H, W)
+    P = OS.make_params('cfg1')
+    tr = Trainer('cfg1', device, state_dicts=_oracle_params_as_state_dicts(P))
+    oopt = OS.Adam(OS.all_params(P), HP['lr'], HP['beta1'], HP['beta2'])
+    dt, dr, dK, dKi = tgt.to(device), [r.to(device) for r in refs], K.to(device), Kinv.to(device)
+    for s in range(steps):
+        lo, _ = OS.train_step('cfg1', P, oopt, tgt, refs, K, Kinv)
+        lc, _ = tr.step(dt, dr, dK, dKi)
+        assert_close(lc, lo, 2e-4, f'cfg1 loss step {s}')
+        if s == 0:
+            for net in ('disp', 'pose'):
+                for name, p in tr.nets[net].named_parameters():
+                    g = P[net][name].grad
+                    if g is None:
+                        continue
+                    if name in ('conv1.0.weight', 'conv1.2.weight', 'conv4.0.conv1.weight', 'iconv2.0.conv2.weight',
+                                'predict_disp1.0.weight', 'upconv3.0.weight', 'pose_pred.weight', 'conv7.0.downsample.1.weight'):
+                        assert_close(p._ccb_grad, g, 1e-3, f'{net}.{name} grad')
+    return tr
+
+
+STEP_CASES_SIM = [case_flat_adam]

@@ -24,10 +24,10 @@ def test_case(case):
     torch.cuda.synchronize()
 
 
-def test_full_size_rigid_loss_vs_oracle_on_device():
-    """BASELINE.json size (b4, 256x832, 6 levels): product vs the oracle's torch ops run on the GPU
-    with TF32 off (the CPU oracle needs ~2 s per call at this size; kept for the fixtures above)."""
-    KC.case_rigid_loss_oracle(torch.device('cuda:0'), B=4, H=256, W=832, NL=6, seed=5)
+def test_full_size_rigid_loss_vs_cpu_oracle():
+    """BASELINE.json size (b4, 256x832, 6 levels): product vs the CPU oracle; masks bit-exact."""
+    KC.case_rigid_loss_oracle(torch.device('cuda:0'), B=4, H=256, W=832, NL=6, seed=5, robust=True,
+                              oracle_device=torch.device('cpu'))
     KC.case_occlusion_and_valid_masks(torch.device('cuda:0'), B=4, H=256, W=832, NL=6, seed=5)
 
 
@@ -68,3 +68,14 @@ def test_net_case(case):
 
 def test_conv_big_shapes():
     NC.case_conv_shapes(torch.device('cuda:0'), big=True)
+
+
+from tests import step_cases as SC   # noqa: E402
+
+
+def test_flat_adam():
+    SC.case_flat_adam(torch.device('cuda:0'))
+
+
+def test_train_step_cfg1_vs_oracle():
+    SC.case_step_cfg1(torch.device('cuda:0'))

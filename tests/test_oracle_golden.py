@@ -145,7 +145,7 @@ NTOL = 2e-5   # conv algorithm choice (mkldnn) may differ between module and fun
 
 def test_nets():
     g = golden('nets_small')
-    B, H, W = 2, 64, 128
+    B, H, W = 2, 32, 64
     tgt, refs = synth.frames(B, H, W, seed=40)
     wts = lambda shape, seed: torch.randn(shape, generator=torch.Generator().manual_seed(seed))
     P = N.clone_params(N.disp_params(), requires_grad=True)
@@ -162,7 +162,7 @@ def test_nets():
     assert_close(P['iconv1.0.downsample.1.running_var'], g['disp_rv'], NTOL)
     with torch.no_grad():
         assert_close(N.disp_forward(P, tgt, training=False), g['disp_eval'], NTOL)
-        t2, _ = synth.frames(2, 40, 104, seed=41)
+        t2, _ = synth.frames(2, 24, 40, seed=41)
         P2 = N.clone_params(N.disp_params())
         for i, x in enumerate(N.disp_forward(P2, t2, training=True)):
             assert_close(x, g[f'disp_odd_out{i}'], NTOL)
@@ -171,6 +171,7 @@ def test_nets():
     assert_close(pose, g['pose_out'], NTOL)
     pn = ['conv1.0.weight', 'conv2.0.weight', 'conv8.0.bias', 'pose_pred.weight', 'pose_pred.bias']
     _check_grads(g, 'pose_g_', pn, Pp, torch.autograd.grad((pose * wts(pose.shape, 60)).sum(), [Pp[n] for n in pn]), 2e-4)
+    tgt, refs = synth.frames(1, 64, 64, seed=42)
     Pm = N.clone_params(N.mask_params(), requires_grad=True)
     ms = N.mask_forward(Pm, tgt, refs)
     for i, x in enumerate(ms):

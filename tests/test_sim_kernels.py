@@ -37,3 +37,11 @@ from tests import net_cases as NC   # noqa: E402
 @pytest.mark.parametrize('case', NC.NET_CASES, ids=lambda f: f.__name__)
 def test_net_case(case):
     case(torch.device('cpu'))
+
+
+from tests import step_cases as SC   # noqa: E402
+
+
+@pytest.mark.parametrize('case', SC.STEP_CASES_SIM, ids=lambda f: f.__name__)
+def test_step_case(case):
+    case(torch.device('cpu'))

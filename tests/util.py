@@ -45,3 +45,18 @@ def key_with_stride(d, prefix):
 
 def pick(g, stride):
     return g if stride is None else g.flatten()[::stride]
+
+
+def assert_close_robust(a, b, tol=1e-4, max_outlier_frac=2e-4, what=''):
+    """Full-size variant: the gradient of a bilinear sample is discontinuous where a coordinate lands on
+    an integer pixel, so 1-ulp coordinate differences flip a handful of pixels' gradients - the oracle
+    run on CPU and on GPU disagree with EACH OTHER at ~1e-4 of the level-0 pixels (gpurun diag_masks
+    log, profiles/r01_parity_notes.md).  Require <= tol everywhere except a vanishing fraction."""
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(b.abs().max().item(), 1e-30)
+    err = (a - b).abs() / scale
+    n_bad = int((err > tol).sum().item())
+    allowed = max(2, int(max_outlier_frac * err.numel()))
+    assert n_bad <= allowed, f'{what}: {n_bad} of {err.numel()} elements exceed {tol:.1e} (max {err.max().item():.2e}), allowed {allowed}'

@@ -66,7 +66,7 @@ class ConvDesc(C.Structure):
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
 CONV_FPROP, CONV_DGRAD, CONV_WGRAD = 0, 1, 2
-IMPL_AUTO, IMPL_FFMA, IMPL_TC = 0, 1, 2
+IMPL_AUTO, IMPL_FFMA, IMPL_TC, IMPL_TC_TF32 = 0, 1, 2, 3
 
 _lib = None
 _is_sim = False
@@ -104,6 +104,11 @@ _SIGS = {
     'ccb_conv2d_wgrad': (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _LL, _P]),
     'ccb_act_bwd': (_I, [_P, _P, _P, _LL, _I, _F, _P]),
     'ccb_bias_grad': (_I, [_P, _P, _I, _I, _I, _P]),
+    'ccb_debug_tc_swap_strides': (None, [_I]),
+    'ccb_corr81_fwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'ccb_corr81_bwd': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'ccb_featwarp_fwd': (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    'ccb_featwarp_bwd': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     'ccb_bn_fwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P]),
     'ccb_bn_bwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     'ccb_upsample2x_fwd': (_I, [_P, _P, _I, _I, _I, _P]),

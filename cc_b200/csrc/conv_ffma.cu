@@ -330,12 +330,32 @@ static int fill_conv(ConvArgs& a, const ccb_conv_desc* d) {
     return CCB_OK;
 }
 
+// tensor-core path (conv_tc.cu)
+bool tc_supported(const ccb_conv_desc* d, int op);
+bool tc_profitable(const ccb_conv_desc* d, int op);
+long long tc_workspace_floats(const ccb_conv_desc* d, int op);
+int tc_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float* bias, const float* res, float* y,
+             float* work, long long work_floats, int three, cudaStream_t st);
+int tc_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const float* bias, const float* res, float* dx,
+             float* work, long long work_floats, int three, cudaStream_t st);
+
+// 0: FFMA, 1: tcgen05 3xTF32, 2: tcgen05 single TF32
+static int pick_impl(const ccb_conv_desc* d, int op) {
+    switch (d->impl) {
+        case CCB_CONV_IMPL_FFMA: return 0;
+        case CCB_CONV_IMPL_TC: return tc_supported(d, op) ? 1 : -1;
+        case CCB_CONV_IMPL_TC_TF32: return tc_supported(d, op) ? 2 : -1;
+        default: return tc_profitable(d, op) ? 1 : 0;
+    }
+}
+
 }  // namespace ccb
 
 using namespace ccb;
 
 extern "C" long long ccb_conv_workspace_floats(const ccb_conv_desc* d, int op) {
     if (!d) return -1;
+    if (d->impl != CCB_CONV_IMPL_FFMA && tc_supported(d, op) && pick_impl(d, op) > 0) return tc_workspace_floats(d, op);
     long long numel = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Co * d->Ho * d->Wo
                     : (op == CCB_CONV_DGRAD) ? (long long)d->B * d->Ci * d->Hi * d->Wi
                                              : (long long)d->Co * d->Ci * d->kh * d->kw;
@@ -352,6 +372,11 @@ extern "C" int ccb_conv2d_fprop(const ccb_conv_desc* d, const float* x, const fl
     int rc = fill_conv(a, d);
     if (rc) return rc;
     CCB_REQUIRE(x && w && y, CCB_ERR_ARG, "conv2d_fprop: null pointer");
+    {
+        int impl = pick_impl(d, CCB_CONV_FPROP);
+        CCB_REQUIRE(impl >= 0, CCB_ERR_UNSUPPORTED, "conv2d_fprop: shape not supported by the tensor-core path");
+        if (impl > 0) return tc_fprop(d, x, w, bias, res, y, work, work_floats, impl == 1, (cudaStream_t)stream);
+    }
     a.x = x; a.w = w; a.bias = bias; a.res = res; a.out = y; a.work = work;
     a.M = a.B * a.Ho * a.Wo; a.N = a.Co; a.K = a.Ci * a.kh * a.kw;
     return launch_gemm<MODE_FPROP>(a, (long long)a.M * a.N, work_floats, (cudaStream_t)stream, "conv2d_fprop");
@@ -364,6 +389,11 @@ extern "C" int ccb_conv2d_dgrad(const ccb_conv_desc* d, const float* dy, const f
     int rc = fill_conv(a, d);
     if (rc) return rc;
     CCB_REQUIRE(dy && w && dx, CCB_ERR_ARG, "conv2d_dgrad: null pointer");
+    {
+        int impl = pick_impl(d, CCB_CONV_DGRAD);
+        CCB_REQUIRE(impl >= 0, CCB_ERR_UNSUPPORTED, "conv2d_dgrad: shape not supported by the tensor-core path");
+        if (impl > 0) return tc_dgrad(d, dy, w, bias, res, dx, work, work_floats, impl == 1, (cudaStream_t)stream);
+    }
     a.dy = dy; a.w = w; a.bias = bias; a.res = res; a.out = dx; a.work = work;
     const int s = a.stride;
     for (int py = 0; py < s && py < a.Hi; ++py)

@@ -1,0 +1,473 @@
+// conv_tc.cu - implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
+//
+//   D[128 pixels x N<=128 channels] (fp32, TMEM) += A[128 x 32] (im2col tile) * B[N x 32]^T (weights)
+//
+// * one CTA = one 128-pixel x N-channel output tile; 8 producer/epilogue warps + 1 MMA warp;
+// * A is gathered straight from the NCHW activations (no im2col buffer in HBM): a K-chunk is 4
+//   consecutive input channels of one filter tap, so the 4 loads of a chunk share the tap's bounds
+//   check and are coalesced across the 128 pixels of the tile;
+// * operands are staged in shared memory in the canonical K-major / no-swizzle UMMA layout
+//   [k-chunk][row][16 B] (8-row x 16 B core matrices contiguous, SBO = 128 B, LBO = rows*16 B);
+// * fp32 parity: every fp32 operand is split hi = tf32(x), lo = x - hi and each k-step issues three
+//   kind::tf32 MMAs (hi*hi + lo*hi + hi*lo) into the same TMEM accumulator ("3xTF32", error ~2^-21);
+//   CCB_CONV_IMPL_TC_TF32 issues hi*hi only (what cuDNN does by default for the reference on Ampere+);
+// * 3-stage mbarrier pipeline: producers -> full[s] -> MMA issuer -> tcgen05.commit -> empty[s];
+//   the epilogue reads the accumulator with tcgen05.ld (lane == pixel), adds bias / residual, applies
+//   the activation and stores NCHW (coalesced: consecutive lanes are consecutive pixels).
+//
+// The same kernel serves FPROP, stride-1 DGRAD and the stride-parity classes of strided DGRAD /
+// ConvTranspose2d forward through a per-tap offset table ("generalised fprop").
+#include "ccb_common.cuh"
+
+#ifndef CCB_CPU_SIM
+
+namespace ccb {
+
+constexpr int TC_M = 128;          // pixels per tile (UMMA M)
+constexpr int TC_NMAX = 128;       // channels per tile (UMMA N <= 128)
+constexpr int TC_KC = 8;           // 16-byte k-chunks per stage (K = 32 fp32 per stage)
+constexpr int TC_STAGES = 3;
+constexpr int TC_PRODUCERS = 256;
+constexpr int TC_THREADS = TC_PRODUCERS + 32;
+constexpr int TC_MAX_TAPS = 49;
+
+struct TcArgs {
+    const float* x;        // input activations [B, Cin, Hin, Win]
+    const float* wp;       // prepared weights [N][Kp]  (k = tap * cpad + c, zero padded)
+    const float* bias;
+    const float* res;
+    float* out;            // [B, N_total, Hout, Wout]
+    int B, Cin, Hin, Win;  // gathered tensor
+    int Ntot;              // output channels
+    int Hout, Wout;        // full output tensor size
+    int Hc, Wc;            // output pixel grid of this launch (== Hout, Wout unless a parity class)
+    int out_stride, out_oy, out_ox;   // y_out = oy * out_stride + out_oy
+    int in_stride;         // iy = oy * in_stride + off_y[tap]
+    int ntaps, cpad, Kp;   // taps in this launch, channels padded to 4, Kp = roundup(ntaps*cpad, 32)
+    int M;                 // B * Hc * Wc
+    int act;
+    float slope;
+    int three;             // 1: 3xTF32, 0: single TF32
+    int swap_lbo_sbo;      // debug: swap the descriptor strides (layout probe)
+    signed char off_y[TC_MAX_TAPS], off_x[TC_MAX_TAPS];
+};
+
+// ---- PTX helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded spin: a protocol bug traps (the launch fails) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try(bar, parity)) {
+        if (++spins > (1u << 26)) asm volatile("trap;");
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor for a [chunk][rows][16 B] tile (rows = 128)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;      // descriptor version 1 (Blackwell)
+    return d;                    // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+
+__device__ __forceinline__ float tc_act(float v, int act, float slope) {
+    switch (act) {
+        case CCB_ACT_RELU: return fmaxf(v, 0.f);
+        case CCB_ACT_LEAKY: return v > 0.f ? v : v * slope;
+        case CCB_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        default: return v;
+    }
+}
+
+constexpr int TC_TILE_BYTES = TC_KC * TC_M * 16;                   // one operand copy of one stage: 16 KB
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                  // A hi, A lo, B hi, B lo
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;   // + barriers / tmem slot / alignment slack
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint64_t* full_bar = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + TC_STAGES;
+    uint64_t* accum_bar = empty_bar + TC_STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * TC_M, n0 = blockIdx.y * TC_NMAX;
+    const int ntile = min(TC_NMAX, a.Ntot - n0);
+    const int umma_n = (ntile + 15) & ~15;
+    const int ktiles = a.Kp / (TC_KC * 4);
+    const long long HWin = (long long)a.Hin * a.Win;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ===================== producers =====================
+        const int r = tid & 127, half = tid >> 7;
+        const int m = m0 + r;
+        const bool mvalid = m < a.M;
+        int b = 0, oy = 0, ox = 0;
+        if (mvalid) {
+            int hw = a.Hc * a.Wc;
+            b = m / hw;
+            int rem = m - b * hw;
+            oy = rem / a.Wc;
+            ox = rem - oy * a.Wc;
+        }
+        const float* xb = a.x + (long long)b * a.Cin * HWin;
+        const int iy0 = oy * a.in_stride, ix0 = ox * a.in_stride;
+        const int cpt = a.cpad >> 2;                 // chunks per tap
+        const int nchunks = a.ntaps * cpt;           // real chunks; the rest of Kp is zero padding
+        for (int it = 0; it < ktiles; ++it) {
+            const int s = it % TC_STAGES;
+            if (it >= TC_STAGES) mbar_wait(&empty_bar[s], ((it / TC_STAGES) - 1) & 1);
+            unsigned char* st = smem + s * TC_STAGE_BYTES;
+            float4* a_hi = (float4*)st;
+            float4* a_lo = (float4*)(st + TC_TILE_BYTES);
+            float4* b_hi = (float4*)(st + 2 * TC_TILE_BYTES);
+            float4* b_lo = (float4*)(st + 3 * TC_TILE_BYTES);
+            // ---- A: 4 chunks of this thread's pixel row
+            float av[4][4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c = half * 4 + cc;
+                const int q = it * TC_KC + c;
+                av[cc][0] = av[cc][1] = av[cc][2] = av[cc][3] = 0.f;
+                if (mvalid && q < nchunks) {
+                    const int tap = q / cpt, c4 = q - tap * cpt;
+                    const int iy = iy0 + a.off_y[tap], ix = ix0 + a.off_x[tap];
+                    if (iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) {
+                        const float* p = xb + (long long)(c4 * 4) * HWin + (long long)iy * a.Win + ix;
+                        const int nv = a.Cin - c4 * 4;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < nv) av[cc][j] = __ldg(p + j * HWin);
+                    }
+                }
+            }
+            // ---- B: 4 float4 of the prepared weight tile
+            float4 bv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = tid + j * TC_PRODUCERS;           // 0 .. 1023
+                const int c = ((idx >> 8) << 1) | (idx & 1);      // idx / (2*128) * 2 + (idx & 1)
+                const int n = (idx >> 1) & 127;
+                bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n < ntile) bv[j] = __ldg((const float4*)(a.wp + (long long)(n0 + n) * a.Kp + it * (TC_KC * 4) + c * 4));
+            }
+            // ---- split + store
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c = half * 4 + cc;
+                float4 h, l;
+                h.x = tf32_hi(av[cc][0]); h.y = tf32_hi(av[cc][1]); h.z = tf32_hi(av[cc][2]); h.w = tf32_hi(av[cc][3]);
+                l.x = av[cc][0] - h.x; l.y = av[cc][1] - h.y; l.z = av[cc][2] - h.z; l.w = av[cc][3] - h.w;
+                a_hi[c * TC_M + r] = h;
+                a_lo[c * TC_M + r] = l;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = tid + j * TC_PRODUCERS;
+                const int c = ((idx >> 8) << 1) | (idx & 1);
+                const int n = (idx >> 1) & 127;
+                float4 h, l;
+                h.x = tf32_hi(bv[j].x); h.y = tf32_hi(bv[j].y); h.z = tf32_hi(bv[j].z); h.w = tf32_hi(bv[j].w);
+                l.x = bv[j].x - h.x; l.y = bv[j].y - h.y; l.z = bv[j].z - h.z; l.w = bv[j].w - h.w;
+                b_hi[c * TC_M + n] = h;
+                b_lo[c * TC_M + n] = l;
+            }
+            fence_proxy_async();
+            mbar_arrive(&full_bar[s]);
+        }
+        // ===================== epilogue =====================
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int q4 = warp & 3, colhalf = warp >> 2;
+        const int em = m0 + q4 * 32 + lane;
+        const bool evalid = em < a.M;
+        long long obase = 0;
+        if (evalid) {
+            int hw = a.Hc * a.Wc;
+            int eb = em / hw;
+            int rem = em - eb * hw;
+            int eoy = rem / a.Wc, eox = rem - eoy * a.Wc;
+            obase = (long long)eb * a.Ntot * a.Hout * a.Wout + (long long)(eoy * a.out_stride + a.out_oy) * a.Wout +
+                    (eox * a.out_stride + a.out_ox);
+        }
+        const long long HWout = (long long)a.Hout * a.Wout;
+        for (int cg = colhalf; cg * 16 < umma_n; cg += 2) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(cg * 16), v);
+            if (evalid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + cg * 16 + j;
+                    if (n < a.Ntot && cg * 16 + j < ntile) {
+                        float o = v[j];
+                        const long long off = obase + (long long)n * HWout;
+                        if (a.bias) o += __ldg(a.bias + n);
+                        if (a.res) o += __ldg(a.res + off);
+                        a.out[off] = tc_act(o, a.act, a.slope);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ===================== MMA issuer (one thread) =====================
+        // instruction descriptor: D fp32, A/B tf32, both K-major, N = umma_n, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+        const uint32_t lbo = a.swap_lbo_sbo ? 128u : (uint32_t)(TC_M * 16);
+        const uint32_t sbo = a.swap_lbo_sbo ? (uint32_t)(TC_M * 16) : 128u;
+        for (int it = 0; it < ktiles; ++it) {
+            const int s = it % TC_STAGES;
+            mbar_wait(&full_bar[s], (it / TC_STAGES) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t base = smem_u32(smem + s * TC_STAGE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < TC_KC / 2; ++ks) {
+                    const uint32_t koff = (uint32_t)ks * 2u * (uint32_t)(TC_M * 16);
+                    const uint64_t ah = make_desc(base + koff, lbo, sbo);
+                    const uint64_t al = make_desc(base + TC_TILE_BYTES + koff, lbo, sbo);
+                    const uint64_t bh = make_desc(base + 2 * TC_TILE_BYTES + koff, lbo, sbo);
+                    const uint64_t bl = make_desc(base + 3 * TC_TILE_BYTES + koff, lbo, sbo);
+                    umma_tf32(tmem_base, ah, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                    if (a.three) {
+                        umma_tf32(tmem_base, al, bh, idesc, 1u);
+                        umma_tf32(tmem_base, ah, bl, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty_bar[s]);                 // frees the stage when these MMAs have read it
+                if (it == ktiles - 1) umma_commit(accum_bar);
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 128);
+    }
+}
+
+// Weight re-layout: wp[n][t*cpad + c] = w[(co,ci) by mode][tap(t)], zero padded to Kp.
+//   mode 0 (fprop): n = co, c = ci : w[n][c][tap]        mode 1 (dgrad): n = ci, c = co : w[c][n][tap]
+struct PrepArgs {
+    const float* w;
+    float* wp;
+    int N, Cc, KK, ntaps, cpad, Kp, mode, Ci;
+    signed char tap_index[TC_MAX_TAPS];
+};
+
+__global__ void __launch_bounds__(256) wprep_kernel(const PrepArgs a) {
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)a.N * a.Kp) return;
+    int n = (int)(i / a.Kp), k = (int)(i - (long long)n * a.Kp);
+    int t = k / a.cpad, c = k - t * a.cpad;
+    float v = 0.f;
+    if (t < a.ntaps && c < a.Cc) {
+        int tap = a.tap_index[t];
+        v = (a.mode == 0) ? __ldg(a.w + ((long long)n * a.Cc + c) * a.KK + tap)
+                          : __ldg(a.w + ((long long)c * a.Ci + n) * a.KK + tap);
+    }
+    a.wp[i] = v;
+}
+
+static int roundup(int v, int m) { return (v + m - 1) / m * m; }
+
+// One generalised-fprop launch (+ its weight preparation).  Returns CCB_OK or an error.
+static int launch_tc(TcArgs& a, const float* w, int mode, int N, int Cc, int KK, int Ci, const signed char* tap_index,
+                     float* work, long long work_floats, cudaStream_t st) {
+    a.cpad = roundup(Cc, 4);
+    a.Kp = roundup(a.ntaps * a.cpad, TC_KC * 4);
+    if (a.Kp == 0) a.Kp = TC_KC * 4;      // a parity class without taps still runs one all-zero k-tile
+    CCB_REQUIRE((long long)N * a.Kp <= work_floats, CCB_ERR_ARG, "conv_tc: workspace too small (%lld < %lld floats)",
+                work_floats, (long long)N * a.Kp);
+    PrepArgs p;
+    p.w = w; p.wp = work; p.N = N; p.Cc = Cc; p.KK = KK; p.ntaps = a.ntaps; p.cpad = a.cpad; p.Kp = a.Kp; p.mode = mode; p.Ci = Ci;
+    for (int t = 0; t < a.ntaps; ++t) p.tap_index[t] = tap_index[t];
+    long long tot = (long long)N * a.Kp;
+    CCB_LAUNCH(wprep_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, p);
+    int rc = check_launch("conv_tc wprep");
+    if (rc) return rc;
+    a.wp = work;
+    a.Ntot = N;
+    { static bool once = false; if (!once) { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); once = true; } }
+    dim3 grid(cdiv(a.M, TC_M), cdiv(N, TC_NMAX));
+    CCB_LAUNCH(conv_tc_kernel, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, a);
+    return check_launch("conv_tc");
+}
+
+static int g_tc_swap = 0;
+
+// Shape gate: which problems take the tensor-core path under CCB_CONV_IMPL_AUTO
+bool tc_supported(const ccb_conv_desc* d, int op) {
+    if (d->kh != d->kw || d->kh * d->kw > TC_MAX_TAPS) return false;
+    if (op == CCB_CONV_WGRAD) return false;
+    return true;
+}
+bool tc_profitable(const ccb_conv_desc* d, int op) {
+    if (!tc_supported(d, op)) return false;
+    long long M = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Ho * d->Wo : (long long)d->B * d->Hi * d->Wi;
+    int N = (op == CCB_CONV_FPROP) ? d->Co : d->Ci;
+    int Cc = (op == CCB_CONV_FPROP) ? d->Ci : d->Co;
+    return M >= 1024 && N >= 16 && Cc * d->kh * d->kw >= 32;
+}
+
+long long tc_workspace_floats(const ccb_conv_desc* d, int op) {
+    int N = (op == CCB_CONV_FPROP) ? d->Co : d->Ci;
+    int Cc = (op == CCB_CONV_FPROP) ? d->Ci : d->Co;
+    return (long long)N * roundup(d->kh * d->kw * roundup(Cc, 4), 32);
+}
+
+int tc_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float* bias, const float* res, float* y,
+             float* work, long long work_floats, int three, cudaStream_t st) {
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.bias = bias; a.res = res; a.out = y;
+    a.B = d->B; a.Cin = d->Ci; a.Hin = d->Hi; a.Win = d->Wi;
+    a.Hout = d->Ho; a.Wout = d->Wo; a.Hc = d->Ho; a.Wc = d->Wo;
+    a.out_stride = 1; a.out_oy = 0; a.out_ox = 0; a.in_stride = d->stride;
+    a.ntaps = d->kh * d->kw;
+    a.M = d->B * d->Ho * d->Wo;
+    a.act = d->act; a.slope = d->slope; a.three = three; a.swap_lbo_sbo = g_tc_swap;
+    signed char tix[TC_MAX_TAPS];
+    for (int ky = 0; ky < d->kh; ++ky)
+        for (int kx = 0; kx < d->kw; ++kx) {
+            int t = ky * d->kw + kx;
+            a.off_y[t] = (signed char)(ky - d->pad);
+            a.off_x[t] = (signed char)(kx - d->pad);
+            tix[t] = (signed char)t;
+        }
+    return launch_tc(a, w, 0, d->Co, d->Ci, d->kh * d->kw, d->Ci, tix, work, work_floats, st);
+}
+
+// dx[b,ci,iy,ix] = sum_{co,ky,kx} dy[b,co,(iy+p-ky)/s,(ix+p-kx)/s] w[co,ci,ky,kx]   (one launch per parity class)
+int tc_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const float* bias, const float* res, float* dx,
+             float* work, long long work_floats, int three, cudaStream_t st) {
+    const int s = d->stride;
+    for (int py = 0; py < s && py < d->Hi; ++py)
+        for (int px = 0; px < s && px < d->Wi; ++px) {
+            TcArgs a;
+            memset(&a, 0, sizeof(a));
+            a.x = dy; a.bias = bias; a.res = res; a.out = dx;
+            a.B = d->B; a.Cin = d->Co; a.Hin = d->Ho; a.Win = d->Wo;
+            a.Hout = d->Hi; a.Wout = d->Wi;
+            a.Hc = (d->Hi - py + s - 1) / s; a.Wc = (d->Wi - px + s - 1) / s;
+            a.out_stride = s; a.out_oy = py; a.out_ox = px; a.in_stride = 1;
+            a.M = d->B * a.Hc * a.Wc;
+            a.act = d->act; a.slope = d->slope; a.three = three; a.swap_lbo_sbo = g_tc_swap;
+            signed char tix[TC_MAX_TAPS];
+            int nt = 0;
+            for (int ky = 0; ky < d->kh; ++ky) {
+                if ((py + d->pad - ky) % s != 0) continue;
+                for (int kx = 0; kx < d->kw; ++kx) {
+                    if ((px + d->pad - kx) % s != 0) continue;
+                    // oy = (iy + p - ky)/s = jy + (py + p - ky)/s   (exact division, may be negative)
+                    a.off_y[nt] = (signed char)((py + d->pad - ky) / s);
+                    a.off_x[nt] = (signed char)((px + d->pad - kx) / s);
+                    tix[nt] = (signed char)(ky * d->kw + kx);
+                    ++nt;
+                }
+            }
+            a.ntaps = nt;
+            int rc = launch_tc(a, w, 1, d->Ci, d->Co, d->kh * d->kw, d->Ci, tix, work, work_floats, st);
+            if (rc) return rc;
+        }
+    return CCB_OK;
+}
+
+void tc_set_debug_swap(int v) { g_tc_swap = v; }
+
+}  // namespace ccb
+
+extern "C" void ccb_debug_tc_swap_strides(int v) { ccb::tc_set_debug_swap(v); }
+
+#else   // CCB_CPU_SIM: no tensor cores in the CPU execution-model simulator
+
+namespace ccb {
+bool tc_supported(const ccb_conv_desc*, int) { return false; }
+bool tc_profitable(const ccb_conv_desc*, int) { return false; }
+long long tc_workspace_floats(const ccb_conv_desc*, int) { return 0; }
+int tc_fprop(const ccb_conv_desc*, const float*, const float*, const float*, const float*, float*, float*, long long, int,
+             cudaStream_t) { return CCB_ERR_UNSUPPORTED; }
+int tc_dgrad(const ccb_conv_desc*, const float*, const float*, const float*, const float*, float*, float*, long long, int,
+             cudaStream_t) { return CCB_ERR_UNSUPPORTED; }
+}  // namespace ccb
+extern "C" void ccb_debug_tc_swap_strides(int) {}
+
+#endif

@@ -108,8 +108,9 @@ __device__ __forceinline__ Proj project(const Cam& cm, float x, float y, float d
 // pose2flow tail, reference inverse_warp.py:217-218
 __device__ __forceinline__ void coords_to_flow(const Cam& cm, float Xn, float Yn, float x, float y,
                                                float& u, float& v) {
-    u = __fsub_rn(__fmul_rn(cm.w1, __fadd_rn(__fdiv_rn(Xn, 2.f), 0.5f)), x);
-    v = __fsub_rn(__fmul_rn(cm.h1, __fadd_rn(__fdiv_rn(Yn, 2.f), 0.5f)), y);
+    // Xn / 2.0 == Xn * 0.5 exactly (power of two): no IEEE-division sequence needed
+    u = __fsub_rn(__fmul_rn(cm.w1, __fadd_rn(__fmul_rn(Xn, 0.5f), 0.5f)), x);
+    v = __fsub_rn(__fmul_rn(cm.h1, __fadd_rn(__fmul_rn(Yn, 0.5f), 0.5f)), y);
 }
 
 // flow_warp grid, reference inverse_warp.py:181-188
@@ -169,7 +170,7 @@ struct Corners { float v00, v01, v10, v11; };
 
 __device__ __forceinline__ Corners fetch(const float* __restrict__ plane, const Samp& s, int w) {
     Corners c;
-    const float* r0 = plane + (long long)s.y0 * w + s.x0;
+    const float* r0 = plane + (s.y0 * w + s.x0);
     const float* r1 = r0 + w;
     c.v00 = (s.oky0 && s.okx0) ? __ldg(r0) : 0.f;
     c.v01 = (s.oky0 && s.okx1) ? __ldg(r0 + 1) : 0.f;
@@ -190,13 +191,14 @@ __device__ __forceinline__ float interp_dy(const Corners& c, const Samp& s) {
 }
 
 // robust L1 (x^2 + 0.01)^q and its derivative wrt x.  loss_functions.py:18-25
+// (values feed means / gradients, not masks: rsqrt.approx (<= 2 ulp) instead of the IEEE sqrt/div sequences)
 __device__ __forceinline__ float rl1(float x, float q) {
     float a = x * x + 0.01f;
-    return (q == 0.5f) ? sqrtf(a) : powf(a, q);
+    return (q == 0.5f) ? a * rsqrtf(a) : powf(a, q);
 }
 __device__ __forceinline__ float rl1_d(float x, float q) {
     float a = x * x + 0.01f;
-    return (q == 0.5f) ? (x / sqrtf(a)) : (2.f * q * x * powf(a, q - 1.f));
+    return (q == 0.5f) ? (x * rsqrtf(a)) : (2.f * q * x * powf(a, q - 1.f));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
     float* sx = reinterpret_cast<float*>(smem_raw);   // [3][PLANE] target
     float* sy = sx + 3 * T::PLANE;                    // [3][PLANE] warped reference
     float* sH = sy + 3 * T::PLANE;                    // [3][RH*HP]  (SSIM only)
-    __shared__ Cam s_cam[3];                          // 0: scaled cam of ref i; 1,2: unscaled (bw, fw) for occ
+    __shared__ Cam s_cam[2 * CCB_MAX_REFS];           // [i]: level-scaled cam of ref i; [R+i]: unscaled cam (occlusion)
     __shared__ float s_red[4 * 32];
     __shared__ float s_g[CCB_SSIM_TAPS];
 
@@ -53,19 +53,25 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
     int l, b, x0, y0, local;
     locate_block(a, l, b, x0, y0, local);
     const int h = d.h[l], w = d.w[l], R = d.R;
-    const long long hw = (long long)h * w;
+    const int hw = h * w;                              // per-tensor offsets fit 32 bits (<= 2^31 elements)
     const int tid = threadIdx.x;
     const int col = tid & 63, rg = tid >> 6;
     const float w1 = (float)(w - 1), h1 = (float)(h - 1);
     if (tid < CCB_SSIM_TAPS) s_g[tid] = d.taps[tid];
+    // ---- all cameras of this (level, batch) at once: threads 64.. build one each
+    if (MODE == CCB_PHOTO_RIGID && tid >= 64 && tid < 64 + 2 * R) {
+        const int k = tid - 64, i = (k < R) ? k : k - R;
+        make_cam(d.pose + (b * R + i) * 6, d.K + b * 9, d.Kinv + b * 9, (k < R) ? (float)d.H / (float)h : 1.f,
+                 d.rotation_mode, w, h, s_cam[k]);
+    }
 
     // ---- stage the target tile (+halo); zero outside the image == conv zero padding
-    const float* tgt = d.tgt[l] + (long long)b * 3 * hw;
+    const float* tgt = d.tgt[l] + b * 3 * hw;
     for (int idx = tid; idx < T::RH * T::RW; idx += NT) {
         int ry = idx / T::RW, rx = idx - ry * T::RW;
         int gy = y0 - HALO + ry, gx = x0 - HALO + rx;
         bool in = (gy >= 0) && (gy < h) && (gx >= 0) && (gx < w);
-        long long off = (long long)gy * w + gx;
+        int off = gy * w + gx;
 #pragma unroll
         for (int c = 0; c < 3; ++c) sx[c * T::PLANE + ry * T::PITCH + rx] = in ? __ldg(tgt + c * hw + off) : 0.f;
     }
@@ -89,23 +95,37 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
     // consensus accumulators: first rigid error / validity, then the combined rigid error
     float cons_e0[PXT], cons_v0[PXT], cons_cam[PXT];
 
-    for (int i = 0; i < R; ++i) {
-        // ---- per-ref cameras
-        if (MODE == CCB_PHOTO_RIGID) {
-            if (tid == 0) {
-                const float* Kb = d.K + b * 9;
-                const float* Kib = d.Kinv + b * 9;
-                make_cam(d.pose + ((long long)b * R + i) * 6, Kb, Kib, (float)d.H / (float)h, d.rotation_mode, w, h, s_cam[0]);
-                if (d.has_occ) {
-                    int lo = (i < R - 1 - i) ? i : R - 1 - i, hi = R - 1 - lo;
-                    make_cam(d.pose + ((long long)b * R + lo) * 6, Kb, Kib, 1.f, d.rotation_mode, w, h, s_cam[1]);
-                    make_cam(d.pose + ((long long)b * R + hi) * 6, Kb, Kib, 1.f, d.rotation_mode, w, h, s_cam[2]);
+    // ---- occlusion masks of the centre pixels, once per pair (refs i and R-1-i share one: SURVEY F5)
+    bool inimg[PXT];
+    float om_pair[2][PXT];     // (1 - occ) of pair (0,R-1) and pair (1,R-2)
+#pragma unroll
+    for (int j = 0; j < PXT; ++j) {
+        const int py = y0 + rg * PXT + j, px = x0 + col;
+        inimg[j] = (py < h) && (px < w);
+        om_pair[0][j] = om_pair[1][j] = 1.f;
+        if (inimg[j] && d.has_occ && MODE != CCB_PHOTO_CONSENSUS) {
+            const int off = py * w + px;
+            if (MODE == CCB_PHOTO_RIGID) {
+                const float dep = __ldg(d.depth[l] + b * hw + off);
+                float u[CCB_MAX_REFS], v[CCB_MAX_REFS];
+#pragma unroll
+                for (int i = 0; i < CCB_MAX_REFS; ++i) {
+                    Proj pp = project(s_cam[R + i], (float)px, (float)py, dep, false);
+                    coords_to_flow(s_cam[R + i], pp.Xn, pp.Yn, (float)px, (float)py, u[i], v[i]);
                 }
+                om_pair[0][j] = 1.f - occ_mask(u[0], v[0], u[3], v[3]);
+                om_pair[1][j] = 1.f - occ_mask(u[1], v[1], u[2], v[2]);
+            } else {
+                const float* fb = d.flow[l][0] + b * 2 * hw + off;
+                const float* ff = d.flow[l][1] + b * 2 * hw + off;
+                om_pair[0][j] = om_pair[1][j] = 1.f - occ_mask(__ldg(fb), __ldg(fb + hw), __ldg(ff), __ldg(ff + hw));
             }
-            __syncthreads();
         }
+    }
+
+    for (int i = 0; i < R; ++i) {
         // ---- warp the reference into sy over the staged region
-        const float* ref = d.ref[l][i] + (long long)b * 3 * hw;
+        const float* ref = d.ref[l][i] + b * 3 * hw;
         for (int idx = tid; idx < T::RH * T::RW; idx += NT) {
             int ry = idx / T::RW, rx = idx - ry * T::RW;
             int gy = y0 - HALO + ry, gx = x0 - HALO + rx;
@@ -114,12 +134,12 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
                 float Xn, Yn;
                 int pad = CCB_PAD_ZEROS;
                 if (MODE == CCB_PHOTO_RIGID) {
-                    float dep = __ldg(d.depth[l] + (long long)b * hw + (long long)gy * w + gx);
-                    Proj p = project(s_cam[0], (float)gx, (float)gy, dep, d.padding_mode == CCB_PAD_ZEROS);
+                    float dep = __ldg(d.depth[l] + b * hw + gy * w + gx);
+                    Proj p = project(s_cam[i], (float)gx, (float)gy, dep, d.padding_mode == CCB_PAD_ZEROS);
                     Xn = p.Xn; Yn = p.Yn;
                     pad = d.padding_mode;
                 } else {
-                    const float* fl = d.flow[l][i] + (long long)b * 2 * hw + (long long)gy * w + gx;
+                    const float* fl = d.flow[l][i] + b * 2 * hw + gy * w + gx;
                     flow_coords((float)gx, (float)gy, __ldg(fl), __ldg(fl + hw), w1, h1, Xn, Yn);
                 }
                 Samp s = make_samp(Xn, Yn, w, h, pad);
@@ -134,36 +154,17 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
 
         // ---- centre-pixel scalars (valid, occlusion, mask)
         float valid[PXT], om[PXT], mk[PXT];   // om = (1-occ)
-        bool inimg[PXT];
+        const int pair = (i == 0 || i == R - 1) ? 0 : 1;
 #pragma unroll
         for (int j = 0; j < PXT; ++j) {
             int py = y0 + rg * PXT + j, px = x0 + col;
-            inimg[j] = (py < h) && (px < w);
             int o = (rg * PXT + j + HALO) * T::PITCH + col + HALO;
             float wv0 = sy[o], wv1 = sy[T::PLANE + o], wv2 = sy[2 * T::PLANE + o];
             valid[j] = ((wv0 != 0.f) || (wv1 != 0.f) || (wv2 != 0.f)) ? 1.f : 0.f;
-            om[j] = 1.f; mk[j] = 1.f;
-            if (inimg[j] && MODE != CCB_PHOTO_CONSENSUS) {
-                long long off = (long long)py * w + px;
-                if (d.has_occ) {
-                    float occ;
-                    if (MODE == CCB_PHOTO_RIGID) {
-                        float dep = __ldg(d.depth[l] + (long long)b * hw + off);
-                        Proj pb = project(s_cam[1], (float)px, (float)py, dep, false);
-                        Proj pf = project(s_cam[2], (float)px, (float)py, dep, false);
-                        float ub, vb, uf, vf;
-                        coords_to_flow(s_cam[1], pb.Xn, pb.Yn, (float)px, (float)py, ub, vb);
-                        coords_to_flow(s_cam[2], pf.Xn, pf.Yn, (float)px, (float)py, uf, vf);
-                        occ = occ_mask(ub, vb, uf, vf);
-                    } else {
-                        const float* fb = d.flow[l][0] + (long long)b * 2 * hw + off;
-                        const float* ff = d.flow[l][1] + (long long)b * 2 * hw + off;
-                        occ = occ_mask(__ldg(fb), __ldg(fb + hw), __ldg(ff), __ldg(ff + hw));
-                    }
-                    om[j] = 1.f - occ;
-                }
-                if (d.has_mask) mk[j] = __ldg(d.mask[l] + ((long long)b * R + i) * hw + off);
-            }
+            om[j] = pair ? om_pair[1][j] : om_pair[0][j];
+            mk[j] = 1.f;
+            if (inimg[j] && MODE != CCB_PHOTO_CONSENSUS && d.has_mask)
+                mk[j] = __ldg(d.mask[l] + (b * R + i) * hw + py * w + px);
         }
 
         // ---- per-channel SSIM + loss terms
@@ -197,8 +198,8 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
                     if (d.has_mask) gm[j] += rl1_d(df, d.qch) * e + d.wssim * sl;
                     if (SSIM) {
                         float gam = -valid[j] * om[j] * mk[j];
-                        long long off = (long long)(y0 + rg * PXT + j) * w + (x0 + col);
-                        float* dm = d.dmaps[l] + (((long long)b * R + i) * 9 + c * 3) * hw + off;
+                        int off = (y0 + rg * PXT + j) * w + (x0 + col);
+                        float* dm = d.dmaps[l] + ((b * R + i) * 9 + c * 3) * hw + off;
                         dm[0] = gam * dmu2;
                         dm[hw] = gam * deyy;
                         dm[2 * hw] = gam * dexy;
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
                 } else {
                     int py = y0 + rg * PXT + j, px = x0 + col;
                     if ((py < h) && (px < w))
-                        d.target[l][(long long)b * hw + (long long)py * w + px] =
+                        d.target[l][b * hw + py * w + px] =
                             (d.wrig * cons_cam[j] <= (e + 1e-8f)) ? 1.f : 0.f;
                 }
             }
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
 #pragma unroll
             for (int j = 0; j < PXT; ++j) {
                 if (!inimg[j]) continue;
-                long long off = ((long long)b * R + i) * hw + (long long)(y0 + rg * PXT + j) * w + (x0 + col);
+                int off = (b * R + i) * hw + (y0 + rg * PXT + j) * w + (x0 + col);
                 s_va += valid[j];
                 s_ob += rl1(1.f - valid[j], d.qch);
                 d.vo[l][off] = valid[j] * om[j];
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
                 po[0] = red[0]; po[1] = red[1]; po[2] = red[2]; po[3] = red[3];
             }
         }
-        __syncthreads();   // sy / s_cam reuse
+        __syncthreads();   // sy reuse
     }
 
 }
@@ -249,37 +250,39 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
 // ------------------------------------------------------------------------------------------------
 // Forward finalize: per (level, ref) sums -> oob normalisation, loss terms, total loss.
 // loss_functions.py:48,58-59 / 103,114
-__global__ void photo_fwd_finalize(const PhotoArgs a) {
-    __shared__ float s_red[4 * 32];
-    __shared__ float s_total;
+__global__ void __launch_bounds__(1024) photo_fwd_finalize(const PhotoArgs a) {
+    __shared__ float s_L[CCB_MAX_LEVELS * CCB_MAX_REFS];
     const ccb_photo_desc& d = a.d;
-    if (threadIdx.x == 0) s_total = 0.f;
-    __syncthreads();
-    for (int l = 0; l < d.nlevels; ++l) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int ncombo = d.nlevels * d.R;
+    for (int cb = warp; cb < ncombo; cb += nwarps) {       // one warp per (level, ref): fixed summation order
+        const int l = cb / d.R, i = cb - l * d.R;
         const int nblk = a.blk_off[l + 1] - a.blk_off[l];
-        for (int i = 0; i < d.R; ++i) {
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int k = threadIdx.x; k < nblk; k += blockDim.x) {
-                const float* p = d.partials + ((long long)(a.blk_off[l] + k) * d.R + i) * 4;
-                v[0] += p[0]; v[1] += p[1]; v[2] += p[2]; v[3] += p[3];
-            }
-            block_sum<4>(v, s_red);
-            if (threadIdx.x == 0) {
-                float npx = (float)((long long)d.B * d.h[l] * d.w[l]);
-                float n = 3.f * npx;
-                float oob = npx / v[2];
-                float L = a.omw * oob * (v[0] / n + d.wssim * (v[1] / n)) + d.lambda_oob * (v[3] / npx);
-                float* sc = d.scal + ((long long)l * d.R + i) * 4;
-                sc[0] = a.omw * oob / n;
-                sc[1] = oob;
-                sc[2] = v[2];
-                sc[3] = L;
-                s_total += L;
-            }
-            __syncthreads();
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+        for (int k = lane; k < nblk; k += 32) {
+            const float* p = d.partials + ((long long)(a.blk_off[l] + k) * d.R + i) * 4;
+            v0 += p[0]; v1 += p[1]; v2 += p[2]; v3 += p[3];
+        }
+        v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+        if (lane == 0) {
+            float npx = (float)((long long)d.B * d.h[l] * d.w[l]);
+            float n = 3.f * npx;
+            float oob = npx / v2;
+            float L = a.omw * oob * (v0 / n + d.wssim * (v1 / n)) + d.lambda_oob * (v3 / npx);
+            float* sc = d.scal + (l * d.R + i) * 4;
+            sc[0] = a.omw * oob / n;
+            sc[1] = oob;
+            sc[2] = v2;
+            sc[3] = L;
+            s_L[cb] = L;
         }
     }
-    if (threadIdx.x == 0) d.loss[0] = s_total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int cb = 0; cb < ncombo; ++cb) t += s_L[cb];
+        d.loss[0] = t;
+    }
 }
 
 // ================================================================================================
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(const PhotoArgs a) {
     CCB_DYN_SMEM(smem_raw);
     float* sD = reinterpret_cast<float*>(smem_raw);   // [3][PLANE] dS maps of one channel
     float* sH = sD + 3 * T::PLANE;                    // [3][RH*HP]
-    __shared__ Cam s_cam;
+    __shared__ Cam s_cam[CCB_MAX_REFS];
     __shared__ float s_red[12 * 32];
     __shared__ float s_g[CCB_SSIM_TAPS];
 
@@ -299,13 +302,16 @@ __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(const PhotoArgs a) {
     int l, b, x0, y0, local;
     locate_block(a, l, b, x0, y0, local);
     const int h = d.h[l], w = d.w[l], R = d.R;
-    const long long hw = (long long)h * w;
+    const int hw = h * w;
     const int tid = threadIdx.x;
     const int col = tid & 63, rg = tid >> 6;
     const float w1 = (float)(w - 1), h1 = (float)(h - 1);
     if (tid < CCB_SSIM_TAPS) s_g[tid] = d.taps[tid];
     const float go = __ldg(d.grad_out);
-    const float* tgt = d.tgt[l] + (long long)b * 3 * hw;
+    const float* tgt = d.tgt[l] + b * 3 * hw;
+    if (MODE == CCB_PHOTO_RIGID && tid >= 64 && tid < 64 + R)
+        make_cam(d.pose + (b * R + (tid - 64)) * 6, d.K + b * 9, d.Kinv + b * 9, (float)d.H / (float)h, d.rotation_mode, w, h,
+                 s_cam[tid - 64]);
 
     float gd[PXT];
 #pragma unroll
@@ -313,24 +319,19 @@ __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(const PhotoArgs a) {
     __syncthreads();
 
     for (int i = 0; i < R; ++i) {
-        const float c_l = go * __ldg(d.scal + ((long long)l * R + i) * 4);
+        const float c_l = go * __ldg(d.scal + (l * R + i) * 4);
         const float c_s = c_l * d.wssim;
-        if (MODE == CCB_PHOTO_RIGID) {
-            if (tid == 0)
-                make_cam(d.pose + ((long long)b * R + i) * 6, d.K + b * 9, d.Kinv + b * 9, (float)d.H / (float)h,
-                         d.rotation_mode, w, h, s_cam);
-        }
         // ---- blur the three dS maps of every channel
         float bl[3][3][PXT];
         if (SSIM) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float* dm = d.dmaps[l] + (((long long)b * R + i) * 9 + c * 3) * hw;
+                const float* dm = d.dmaps[l] + ((b * R + i) * 9 + c * 3) * hw;
                 for (int idx = tid; idx < T::RH * T::RW; idx += NT) {
                     int ry = idx / T::RW, rx = idx - ry * T::RW;
                     int gy = y0 - 6 + ry, gx = x0 - 6 + rx;
                     bool in = (gy >= 0) && (gy < h) && (gx >= 0) && (gx < w);
-                    long long off = (long long)gy * w + gx;
+                    int off = gy * w + gx;
                     int o = ry * T::PITCH + rx;
                     sD[o] = in ? __ldg(dm + off) : 0.f;
                     sD[T::PLANE + o] = in ? __ldg(dm + hw + off) : 0.f;
@@ -342,9 +343,9 @@ __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(const PhotoArgs a) {
                 vpass<3>(sH, s_g, bl[c]);
             }
         }
-        __syncthreads();   // s_cam visible; sD/sH free
+        __syncthreads();   // sD/sH free
 
-        const float* ref = d.ref[l][i] + (long long)b * 3 * hw;
+        const float* ref = d.ref[l][i] + b * 3 * hw;
         float acc[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) acc[k] = 0.f;
@@ -352,18 +353,18 @@ __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(const PhotoArgs a) {
         for (int j = 0; j < PXT; ++j) {
             int py = y0 + rg * PXT + j, px = x0 + col;
             if ((py < h) && (px < w)) {
-                long long off = (long long)py * w + px;
-                long long moff = ((long long)b * R + i) * hw + off;
+                int off = py * w + px;
+                int moff = (b * R + i) * hw + off;
                 float Xn, Yn;
                 Proj p;
                 int pad = CCB_PAD_ZEROS;
                 if (MODE == CCB_PHOTO_RIGID) {
-                    float dep = __ldg(d.depth[l] + (long long)b * hw + off);
-                    p = project(s_cam, (float)px, (float)py, dep, d.padding_mode == CCB_PAD_ZEROS);
+                    float dep = __ldg(d.depth[l] + b * hw + off);
+                    p = project(s_cam[i], (float)px, (float)py, dep, d.padding_mode == CCB_PAD_ZEROS);
                     Xn = p.Xn; Yn = p.Yn;
                     pad = d.padding_mode;
                 } else {
-                    const float* fl = d.flow[l][i] + (long long)b * 2 * hw + off;
+                    const float* fl = d.flow[l][i] + b * 2 * hw + off;
                     flow_coords((float)px, (float)py, __ldg(fl), __ldg(fl + hw), w1, h1, Xn, Yn);
                 }
                 Samp s = make_samp(Xn, Yn, w, h, pad);
@@ -384,9 +385,9 @@ __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(const PhotoArgs a) {
                 }
                 float gXn = gix * s.gmx, gYn = giy * s.gmy;
                 if (MODE == CCB_PHOTO_RIGID) {
-                    gd[j] += project_bwd(s_cam, p, gXn, gYn, acc);
+                    gd[j] += project_bwd(s_cam[i], p, gXn, gYn, acc);
                 } else {
-                    float* df = d.d_flow[l][i] + (long long)b * 2 * hw + off;
+                    float* df = d.d_flow[l][i] + b * 2 * hw + off;
                     df[0] = gXn * (2.f / w1);
                     df[hw] = gYn * (2.f / h1);
                 }
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(const PhotoArgs a) {
 #pragma unroll
         for (int j = 0; j < PXT; ++j) {
             int py = y0 + rg * PXT + j, px = x0 + col;
-            if ((py < h) && (px < w)) d.d_depth[l][(long long)b * hw + (long long)py * w + px] = gd[j];
+            if ((py < h) && (px < w)) d.d_depth[l][b * hw + py * w + px] = gd[j];
         }
     }
 }
@@ -536,7 +537,7 @@ extern "C" int ccb_photo_loss_fwd(const ccb_photo_desc* d, ccb_stream_t stream) 
     if (d->mode == CCB_PHOTO_RIGID) rc = ss ? launch_fwd<CCB_PHOTO_RIGID, true>(a, st) : launch_fwd<CCB_PHOTO_RIGID, false>(a, st);
     else rc = ss ? launch_fwd<CCB_PHOTO_FLOW, true>(a, st) : launch_fwd<CCB_PHOTO_FLOW, false>(a, st);
     if (rc) return rc;
-    CCB_LAUNCH(photo_fwd_finalize, dim3(1), dim3(128), 0, st, a);
+    CCB_LAUNCH(photo_fwd_finalize, dim3(1), dim3(1024), 0, st, a);
     return check_launch("photo_fwd_finalize");
 }
 

@@ -119,10 +119,10 @@ __device__ __forceinline__ float ssim_point(float mu1, float exx, float mu2, flo
     float s1 = exx - mu1_sq, s2 = eyy - mu2_sq, s12 = exy - mu12;
     float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2;
     float B1 = mu1_sq + mu2_sq + C1, B2 = s1 + s2 + C2;
-    float inv = 1.f / (B1 * B2);
+    float inv = __fdividef(1.f, B1 * B2);            // B1, B2 >= C1, C2 > 0: fast reciprocal (<= 2 ulp) is safe
     float S = (A1 * A2) * inv;
     dmu2 = 2.f * mu1 * (A2 - A1) * inv - S * 2.f * mu2 * (B2 - B1) * inv;
-    deyy = -S / B2;
+    deyy = -S * __fdividef(1.f, B2);
     dexy = 2.f * A1 * inv;
     return S;
 }

@@ -66,6 +66,7 @@ struct WarpArgs {
     float* d_pose;
     float* pose_partials;
     int B, C, h, w, rot, pad;
+    int b2f_norm;     // 1: Back2Future.warp normalisation 2*(x+u)/max(W-1,1)-1 (back2future.py:305-306)
 };
 
 constexpr int WNT = 256;
@@ -165,6 +166,15 @@ __global__ void rigid_pose_finalize(const WarpArgs a, int nblk) {
     }
 }
 
+__device__ __forceinline__ void warp_coords(const WarpArgs& a, float x, float y, float u, float v, float& Xn, float& Yn) {
+    if (a.b2f_norm) {
+        Xn = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fadd_rn(x, u)), (float)max(a.w - 1, 1)), 1.f);
+        Yn = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fadd_rn(y, v)), (float)max(a.h - 1, 1)), 1.f);
+    } else {
+        flow_coords(x, y, u, v, (float)(a.w - 1), (float)(a.h - 1), Xn, Yn);
+    }
+}
+
 // flow_warp (inverse_warp.py:164-192), any channel count
 __global__ void __launch_bounds__(WNT) flow_warp_fwd_kernel(const WarpArgs a) {
     const int b = blockIdx.y;
@@ -173,8 +183,8 @@ __global__ void __launch_bounds__(WNT) flow_warp_fwd_kernel(const WarpArgs a) {
     if (idx >= hw) return;
     int y = (int)(idx / a.w), x = (int)(idx - (long long)y * a.w);
     float Xn, Yn;
-    flow_coords((float)x, (float)y, __ldg(a.flow + (long long)b * 2 * hw + idx), __ldg(a.flow + (long long)b * 2 * hw + hw + idx),
-                (float)(a.w - 1), (float)(a.h - 1), Xn, Yn);
+    warp_coords(a, (float)x, (float)y, __ldg(a.flow + (long long)b * 2 * hw + idx), __ldg(a.flow + (long long)b * 2 * hw + hw + idx),
+                Xn, Yn);
     Samp s = make_samp(Xn, Yn, a.w, a.h, a.pad);
     const float* im = a.img + (long long)b * a.C * hw;
     for (int c = 0; c < a.C; ++c) a.out[(long long)b * a.C * hw + c * hw + idx] = interp(fetch(im + c * hw, s, a.w), s);
@@ -187,9 +197,9 @@ __global__ void __launch_bounds__(WNT) flow_warp_bwd_kernel(const WarpArgs a) {
     if (idx >= hw) return;
     int y = (int)(idx / a.w), x = (int)(idx - (long long)y * a.w);
     float Xn, Yn;
-    const float w1 = (float)(a.w - 1), h1 = (float)(a.h - 1);
-    flow_coords((float)x, (float)y, __ldg(a.flow + (long long)b * 2 * hw + idx), __ldg(a.flow + (long long)b * 2 * hw + hw + idx),
-                w1, h1, Xn, Yn);
+    const float w1 = (float)max(a.w - 1, 1), h1 = (float)max(a.h - 1, 1);
+    warp_coords(a, (float)x, (float)y, __ldg(a.flow + (long long)b * 2 * hw + idx), __ldg(a.flow + (long long)b * 2 * hw + hw + idx),
+                Xn, Yn);
     Samp s = make_samp(Xn, Yn, a.w, a.h, a.pad);
     const float* im = a.img + (long long)b * a.C * hw;
     float gix = 0.f, giy = 0.f;
@@ -443,6 +453,28 @@ extern "C" int ccb_flow_warp_bwd(const float* img, const float* flow, int B, int
     a.B = B; a.C = C; a.h = h; a.w = w; a.pad = padding_mode;
     CCB_LAUNCH(flow_warp_bwd_kernel, dim3(cdiv(h * w, WNT), B), dim3(WNT), 0, stream, a);
     return check_launch("flow_warp_bwd");
+}
+
+// Back2Future.warp (back2future.py:287-321): border padding, b2f coordinate normalisation
+extern "C" int ccb_featwarp_fwd(const float* x, const float* flow, int B, int C, int h, int w, float* out,
+                                ccb_stream_t stream) {
+    CCB_REQUIRE(x && flow && out, CCB_ERR_ARG, "featwarp_fwd: null pointer");
+    WarpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.img = x; a.flow = flow; a.out = out; a.B = B; a.C = C; a.h = h; a.w = w; a.pad = CCB_PAD_BORDER; a.b2f_norm = 1;
+    CCB_LAUNCH(flow_warp_fwd_kernel, dim3(cdiv(h * w, WNT), B), dim3(WNT), 0, stream, a);
+    return check_launch("featwarp_fwd");
+}
+
+extern "C" int ccb_featwarp_bwd(const float* x, const float* flow, int B, int C, int h, int w, const float* grad_out,
+                                float* d_flow, float* d_x, ccb_stream_t stream) {
+    CCB_REQUIRE(x && flow && grad_out, CCB_ERR_ARG, "featwarp_bwd: null pointer");
+    WarpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.img = x; a.flow = flow; a.grad_out = grad_out; a.d_flow = d_flow; a.d_img = d_x;
+    a.B = B; a.C = C; a.h = h; a.w = w; a.pad = CCB_PAD_BORDER; a.b2f_norm = 1;
+    CCB_LAUNCH(flow_warp_bwd_kernel, dim3(cdiv(h * w, WNT), B), dim3(WNT), 0, stream, a);
+    return check_launch("featwarp_bwd");
 }
 
 static size_t ssim_smem_fwd() { return (size_t)(2 * Tile<6>::PLANE + 3 * Tile<6>::RH * HP) * sizeof(float); }

@@ -299,3 +299,63 @@ def xavier_init_(module, bias_uniform=False):
                     nn.init.uniform_(m.bias.data)
                 else:
                     m.bias.data.zero_()
+
+
+# -------------------------------------------------------------------------------------------------
+# Back2Future operators
+class _Corr81Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f1, f2, reversed_):
+        f1, f2 = _c(f1), _c(f2)
+        B, Cc, h, w = f1.shape
+        out = torch.empty(B, 81, h, w, device=f1.device, dtype=torch.float32)
+        _lib.check(_lib.lib().ccb_corr81_fwd(_lib.ptr(f1), _lib.ptr(f2), _lib.ptr(out), B, Cc, h, w, int(reversed_),
+                                             _lib.stream(f1)), 'corr81_fwd')
+        ctx.save_for_backward(f1, f2)
+        ctx.rev = int(reversed_)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        f1, f2 = ctx.saved_tensors
+        B, Cc, h, w = f1.shape
+        g = _c(g)
+        d1 = torch.empty_like(f1) if ctx.needs_input_grad[0] else None
+        d2 = torch.empty_like(f2) if ctx.needs_input_grad[1] else None
+        if d1 is not None or d2 is not None:
+            _lib.check(_lib.lib().ccb_corr81_bwd(_lib.ptr(f1), _lib.ptr(f2), _lib.ptr(g), _lib.ptr(d1), _lib.ptr(d2), B, Cc,
+                                                 h, w, ctx.rev, _lib.stream(f1)), 'corr81_bwd')
+        return d1, d2, None
+
+
+class _FeatWarpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, flo):
+        x, flo = _c(x), _c(flo)
+        B, Cc, h, w = x.shape
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib().ccb_featwarp_fwd(_lib.ptr(x), _lib.ptr(flo), B, Cc, h, w, _lib.ptr(out), _lib.stream(x)),
+                   'featwarp_fwd')
+        ctx.save_for_backward(x, flo)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, flo = ctx.saved_tensors
+        B, Cc, h, w = x.shape
+        g = _c(g)
+        dx = torch.zeros_like(x) if ctx.needs_input_grad[0] else None
+        df = torch.empty_like(flo) if ctx.needs_input_grad[1] else None
+        _lib.check(_lib.lib().ccb_featwarp_bwd(_lib.ptr(x), _lib.ptr(flo), B, Cc, h, w, _lib.ptr(g), _lib.ptr(df),
+                                               _lib.ptr(dx), _lib.stream(x)), 'featwarp_bwd')
+        return dx, df
+
+
+def corr81(f1, f2, reversed_=False):
+    """correlate(f1, f2).index_select(1, idx_fwd | idx_bwd) of back2future.py:15-25,173-176."""
+    return _Corr81Fn.apply(f1, f2, reversed_)
+
+
+def feat_warp(x, flo):
+    """Model.warp of back2future.py:287-321."""
+    return _FeatWarpFn.apply(x, flo)

@@ -204,7 +204,8 @@ int ccb_bce_bwd(const ccb_bce_desc* d, ccb_stream_t stream);
  * ---------------------------------------------------------------------------------------------- */
 enum { CCB_ACT_NONE = 0, CCB_ACT_RELU = 1, CCB_ACT_LEAKY = 2, CCB_ACT_SIGMOID = 3 };
 enum { CCB_CONV_FPROP = 0, CCB_CONV_DGRAD = 1, CCB_CONV_WGRAD = 2 };
-enum { CCB_CONV_IMPL_AUTO = 0, CCB_CONV_IMPL_FFMA = 1, CCB_CONV_IMPL_TC = 2 };
+enum { CCB_CONV_IMPL_AUTO = 0, CCB_CONV_IMPL_FFMA = 1, CCB_CONV_IMPL_TC = 2 /* tcgen05 3xTF32 (fp32 parity) */,
+       CCB_CONV_IMPL_TC_TF32 = 3 /* tcgen05 single TF32 (cuDNN's default math for the reference) */ };
 typedef struct ccb_conv_desc {
     int B, Ci, Hi, Wi;      /* input  [B,Ci,Hi,Wi] */
     int Co, Ho, Wo;         /* output [B,Co,Ho,Wo]; Ho = (Hi + 2 pad - kh) / stride + 1 */
@@ -224,6 +225,23 @@ int ccb_conv2d_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, fl
 int ccb_act_bwd(const float* dy, const float* y, float* dz, long long numel, int act, float slope,
                 ccb_stream_t stream);
 int ccb_bias_grad(const float* dy, float* db, int B, int C, int plane, ccb_stream_t stream);
+/* bring-up aid: swap the LBO/SBO strides of the UMMA shared-memory descriptors (layout probe) */
+void ccb_debug_tc_swap_strides(int swap);
+
+/* Back2Future operators (models/back2future.py).
+ * corr81: cost volume of correlate() :15-25 (third-party spatial_correlation_sample, kernel 1, patch 9,
+ * zero padded, divided by C) with the reference's channel permutation baked in (reversed=0: idx_fwd,
+ * 1: idx_bwd, :56-59).  f1,f2 [B,C,h,w] -> out [B,81,h,w].   d_f1 / d_f2 may be NULL.
+ * featwarp: Model.warp :287-321 = grid_sample(x, grid+flow, padding border, align_corners False). */
+int ccb_corr81_fwd(const float* f1, const float* f2, float* out, int B, int C, int h, int w, int reversed,
+                   ccb_stream_t stream);
+int ccb_corr81_bwd(const float* f1, const float* f2, const float* grad_out, float* d_f1, float* d_f2, int B,
+                   int C, int h, int w, int reversed, ccb_stream_t stream);
+int ccb_featwarp_fwd(const float* x, const float* flow, int B, int C, int h, int w, float* out,
+                     ccb_stream_t stream);
+/* d_x must be zero-filled by the caller (scatter-add); d_flow / d_x may be NULL */
+int ccb_featwarp_bwd(const float* x, const float* flow, int B, int C, int h, int w, const float* grad_out,
+                     float* d_flow, float* d_x, ccb_stream_t stream);
 
 /* BatchNorm2d over [B,C,plane] (DispResNet6.py:45-52).  training: batch statistics, stats[C][2] =
  * {mean, invstd} saved for backward, running stats updated in place (momentum, unbiased var). */

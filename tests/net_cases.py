@@ -156,8 +156,51 @@ def case_mask_golden(device):
     _check_grads(g, 'mask_g_', mn, mpd, torch.autograd.grad(loss, [mpd[n] for n in mn]), 5e-4)
 
 
+def case_flow_golden(device):
+    """Back2Future module + cost volume + feature warp vs fixtures from the reference net (stub correlation:
+    the third-party op is the one parity-unpinned boundary, oracle/nets.py)."""
+    g = golden('nets_small')
+    tgt, refs = synth.frames(1, 64, 64, seed=42)
+    tgt, refs = tgt.to(device), [r.to(device) for r in refs]
+    fnet = _load(CM.Back2Future(nlevels=6), ON.flow_params(), device)
+    fnet.train()
+    ff, fb, occ = fnet(tgt, refs[1:3])
+    for i in range(6):
+        assert_close(ff[i], g[f'flow_fwd{i}'], 2e-4, f'flow_fwd{i}')
+        assert_close(fb[i], g[f'flow_bwd{i}'], 2e-4, f'flow_bwd{i}')
+    assert_close(occ[0][:, :, ::4, ::4], g['flow_occ0'], 2e-4, 'occ0')
+    assert_close(occ[5], g['flow_occ5'], 2e-4, 'occ5')
+    fn = ['conv1a.0.weight', 'conv1b.2.bias', 'conv6c.0.weight', 'decoder_fwd6.0.weight',
+          'decoder_bwd2.10.weight', 'decoder_fwd2.0.weight', 'decoder_bwd4.4.bias']
+    fpd = dict(fnet.named_parameters())
+    lossf = sum((x * _wts(x.shape, 80 + i, device)).sum() + (y * _wts(x.shape, 80 + i, device)).sum() * 0.5
+                for i, (x, y) in enumerate(zip(ff, fb)))
+    _check_grads(g, 'flow_g_', fn, fpd, torch.autograd.grad(lossf, [fpd[n] for n in fn]), 1e-3)
+    fnet.eval()
+    with torch.no_grad():
+        e = fnet(tgt, refs[1:3])
+        assert_close(e[0][:, :, ::2, ::2], g['flow_eval_fwd'], 2e-4, 'flow eval')
+    # cost volume / feature warp in isolation against the oracle restatement
+    gen = torch.Generator().manual_seed(3)
+    f1 = torch.randn(2, 12, 9, 13, generator=gen).to(device).requires_grad_(True)
+    f2 = torch.randn(2, 12, 9, 13, generator=gen).to(device).requires_grad_(True)
+    for rev, idx in ((False, ON.IDX_FWD), (True, ON.IDX_BWD)):
+        a_ = cnn.corr81(f1, f2, rev)
+        b_ = ON.correlate(f1, f2).index_select(1, torch.tensor(idx, device=device))
+        assert_close(a_, b_, TOL, 'corr81')
+        wt = _wts(a_.shape, 9, device)
+        for x_, y_, nm in zip(torch.autograd.grad((a_ * wt).sum(), [f1, f2]), torch.autograd.grad((b_ * wt).sum(), [f1, f2]), ('df1', 'df2')):
+            assert_close(x_, y_, TOL, 'corr81 ' + nm)
+    flo = (torch.randn(2, 2, 9, 13, generator=gen) * 2).to(device).requires_grad_(True)
+    a_, b_ = cnn.feat_warp(f1, flo), ON.b2f_warp(f1, flo)
+    assert_close(a_, b_, TOL, 'feat_warp')
+    wt = _wts(a_.shape, 10, device)
+    for x_, y_, nm in zip(torch.autograd.grad((a_ * wt).sum(), [f1, flo]), torch.autograd.grad((b_ * wt).sum(), [f1, flo]), ('dx', 'dflow')):
+        assert_close(x_, y_, TOL, 'feat_warp ' + nm)
+
+
 def smoke_case(device):
     case_conv_shapes(device)
 
 
-NET_CASES = [case_conv_shapes, case_bn_upsample, case_disp_pose_golden, case_mask_golden]
+NET_CASES = [case_conv_shapes, case_bn_upsample, case_disp_pose_golden, case_mask_golden, case_flow_golden]

@@ -164,6 +164,7 @@ static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; retu
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
+static inline float __fdividef(float a, float b) { return a / b; }
 // (__expf/__logf/__powf exist in glibc as internal symbols with the right meaning)
 static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 static inline float __saturatef(float a) { return a < 0 ? 0.f : (a > 1 ? 1.f : a); }

@@ -281,6 +281,33 @@ def profile_pass(trainer, tgt, refs, K, Kinv, steps=2):
 
 
 # ---------------------------------------------------------------------------------------------------
+def pick_cpu_threads():
+    """torch CPU ops collapse when every tiny op fans out over 100+ threads (measured: 180 s/step at 128 threads
+    vs ~1.3 s at 8): calibrate on a proxy (conv fwd+bwd + one loss-layer call) and use the fastest setting."""
+    import torch.nn.functional as F
+    from cc_b200 import synth
+    from oracle import losses as OL
+    n = os.cpu_count() or 1
+    cands = sorted({c for c in (4, 8, 16, 32, 64, n) if c <= n})
+    x = torch.randn(2, 32, 64, 208, requires_grad=True)
+    w = torch.randn(32, 32, 3, 3, requires_grad=True)
+    s = synth.sample(2, 64, 208, seed=3, nlevels=3)
+    best, best_t = cands[0], float('inf')
+    for c in cands:
+        torch.set_num_threads(c)
+        ts = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            F.conv2d(x, w, None, 1, 1).sum().backward()
+            d = [t.clone().requires_grad_(True) for t in s['depth']]
+            OL.photometric_reconstruction_loss(s['tgt'], s['refs'], s['K'], s['Kinv'], d, [None] * 3, s['pose'], wssim=0.9).backward()
+            ts.append(time.perf_counter() - t0)
+        if min(ts) < best_t:
+            best, best_t = c, min(ts)
+    torch.set_num_threads(best)
+    return best, n
+
+
 def _oracle_step_timer(cfg, B, threads):
     from cc_b200 import synth
     from oracle import step as OS
@@ -299,7 +326,7 @@ def _oracle_step_timer(cfg, B, threads):
 
 def cpu_baseline(cfg, budget_s=25.0):
     """The oracle port of the reference step on the host cores, bounded to ~budget_s of CPU work."""
-    threads = os.cpu_count() or 1
+    threads, ncores = pick_cpu_threads()
     B = 2
     run = _oracle_step_timer(cfg, B, threads)
     t_first = run()                      # warm-up (allocator, thread pool)
@@ -309,7 +336,7 @@ def cpu_baseline(cfg, budget_s=25.0):
     ts.sort()
     t = ts[len(ts) // 2]
     return {'value': B / t, 'unit': 'triplets/s', 'cores': threads, 'kind': 'port',
-            'sample': '%s oracle step (fwd+bwd+Adam) at b%d 256x832x6lvl, torch CPU fp32, median of %d after 1 warm-up' % (cfg, B, len(ts)),
+            'sample': '%s oracle step (fwd+bwd+Adam) at b%d 256x832x6lvl, torch CPU fp32, %d threads (fastest of a calibration sweep; box has %d cores), median of %d after 1 warm-up' % (cfg, B, threads, ncores, len(ts)),
             's_per_step': t}
 
 
@@ -319,7 +346,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return None
-    threads = os.cpu_count() or 1
+    threads, ncores = pick_cpu_threads()
     B = 2
     run = _oracle_step_timer(args.cfg, B, threads)
     probe = run()
@@ -340,7 +367,7 @@ def run_reference(args):
             'config': {'workload': CFG_WORKLOAD[args.cfg], 'sample_batch_per_step': B, 'frame': '%dx%d' % (H, W),
                        'levels': NLEVELS, 'device': 'host CPU'},
             'cpu_baseline': {'value': v, 'unit': 'triplets/s', 'cores': threads, 'kind': 'port',
-                             'sample': 'oracle %s step at b%d per step, %d steps' % (args.cfg, B, args.steps)},
+                             'sample': 'oracle %s step at b%d per step, %d steps, %d threads (fastest of a sweep; %d cores)' % (args.cfg, B, args.steps, threads, ncores)},
             'e2e': {'value': v, 'unit': 'triplets/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
 
 

@@ -49,6 +49,7 @@ struct TcArgs {
     float slope;
     int three;             // 1: 3xTF32, 0: single TF32
     int swap_lbo_sbo;      // debug: swap the descriptor strides (layout probe)
+    int swz;               // 0: K-major no-swizzle [chunk][row][16B]; 1: K-major SWIZZLE_128B [row][128B], chunk ^= row&7
     signed char off_y[TC_MAX_TAPS], off_x[TC_MAX_TAPS];
 };
 
@@ -125,13 +126,18 @@ __device__ __forceinline__ float tf32_hi(float x) {
 }
 
 // K-major, no-swizzle shared-memory matrix descriptor for a [chunk][rows][16 B] tile (rows = 128)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 0) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;      // descriptor version 1 (Blackwell)
-    return d;                    // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+    d |= (uint64_t)(layout_type & 7) << 61;   // 0 SWIZZLE_NONE, 2 SWIZZLE_128B
+    return d;                    // base_offset 0, lbo_mode 0
+}
+// float4 index of (row, 16-byte chunk) inside one operand tile
+__device__ __forceinline__ int tile_idx(int row, int chunk, int swz) {
+    return swz ? (row * TC_KC + (chunk ^ (row & 7))) : (chunk * TC_M + row);
 }
 
 __device__ __forceinline__ float tc_act(float v, int act, float slope) {
@@ -145,11 +151,11 @@ __device__ __forceinline__ float tc_act(float v, int act, float slope) {
 
 constexpr int TC_TILE_BYTES = TC_KC * TC_M * 16;                   // one operand copy of one stage: 16 KB
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                  // A hi, A lo, B hi, B lo
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;   // + barriers / tmem slot / alignment slack
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 2048;   // + barriers / tmem slot / alignment slack
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms are 1 KB
     uint64_t* full_bar = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + TC_STAGES;
     uint64_t* accum_bar = empty_bar + TC_STAGES;
@@ -234,8 +240,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
                 float4 h, l;
                 h.x = tf32_hi(av[cc][0]); h.y = tf32_hi(av[cc][1]); h.z = tf32_hi(av[cc][2]); h.w = tf32_hi(av[cc][3]);
                 l.x = av[cc][0] - h.x; l.y = av[cc][1] - h.y; l.z = av[cc][2] - h.z; l.w = av[cc][3] - h.w;
-                a_hi[c * TC_M + r] = h;
-                a_lo[c * TC_M + r] = l;
+                a_hi[tile_idx(r, c, a.swz)] = h;
+                a_lo[tile_idx(r, c, a.swz)] = l;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -245,8 +251,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
                 float4 h, l;
                 h.x = tf32_hi(bv[j].x); h.y = tf32_hi(bv[j].y); h.z = tf32_hi(bv[j].z); h.w = tf32_hi(bv[j].w);
                 l.x = bv[j].x - h.x; l.y = bv[j].y - h.y; l.z = bv[j].z - h.z; l.w = bv[j].w - h.w;
-                b_hi[c * TC_M + n] = h;
-                b_lo[c * TC_M + n] = l;
+                b_hi[tile_idx(n, c, a.swz)] = h;
+                b_lo[tile_idx(n, c, a.swz)] = l;
             }
             fence_proxy_async();
             mbar_arrive(&full_bar[s]);
@@ -289,8 +295,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
         // ===================== MMA issuer (one thread) =====================
         // instruction descriptor: D fp32, A/B tf32, both K-major, N = umma_n, M = 128
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-        const uint32_t lbo = a.swap_lbo_sbo ? 128u : (uint32_t)(TC_M * 16);
-        const uint32_t sbo = a.swap_lbo_sbo ? (uint32_t)(TC_M * 16) : 128u;
+        uint32_t lbo = a.swz ? 16u : (uint32_t)(TC_M * 16);
+        uint32_t sbo = a.swz ? 1024u : 128u;
+        if (a.swap_lbo_sbo) { uint32_t t = lbo; lbo = sbo; sbo = t; }
+        const uint32_t ltype = a.swz ? 2u : 0u;
+        const uint32_t kstep_bytes = a.swz ? 32u : 2u * (uint32_t)(TC_M * 16);
         for (int it = 0; it < ktiles; ++it) {
             const int s = it % TC_STAGES;
             mbar_wait(&full_bar[s], (it / TC_STAGES) & 1);
@@ -299,11 +308,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
                 const uint32_t base = smem_u32(smem + s * TC_STAGE_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < TC_KC / 2; ++ks) {
-                    const uint32_t koff = (uint32_t)ks * 2u * (uint32_t)(TC_M * 16);
-                    const uint64_t ah = make_desc(base + koff, lbo, sbo);
-                    const uint64_t al = make_desc(base + TC_TILE_BYTES + koff, lbo, sbo);
-                    const uint64_t bh = make_desc(base + 2 * TC_TILE_BYTES + koff, lbo, sbo);
-                    const uint64_t bl = make_desc(base + 3 * TC_TILE_BYTES + koff, lbo, sbo);
+                    const uint32_t koff = (uint32_t)ks * kstep_bytes;
+                    const uint64_t ah = make_desc(base + koff, lbo, sbo, ltype);
+                    const uint64_t al = make_desc(base + TC_TILE_BYTES + koff, lbo, sbo, ltype);
+                    const uint64_t bh = make_desc(base + 2 * TC_TILE_BYTES + koff, lbo, sbo, ltype);
+                    const uint64_t bl = make_desc(base + 3 * TC_TILE_BYTES + koff, lbo, sbo, ltype);
                     umma_tf32(tmem_base, ah, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
                     if (a.three) {
                         umma_tf32(tmem_base, al, bh, idesc, 1u);
@@ -373,6 +382,7 @@ static int launch_tc(TcArgs& a, const float* w, int mode, int N, int Cc, int KK,
 }
 
 static int g_tc_swap = 0;
+static int g_tc_swz = 0;
 
 // Shape gate: which problems take the tensor-core path under CCB_CONV_IMPL_AUTO
 bool tc_supported(const ccb_conv_desc* d, int op) {
@@ -404,7 +414,7 @@ int tc_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float
     a.out_stride = 1; a.out_oy = 0; a.out_ox = 0; a.in_stride = d->stride;
     a.ntaps = d->kh * d->kw;
     a.M = d->B * d->Ho * d->Wo;
-    a.act = d->act; a.slope = d->slope; a.three = three; a.swap_lbo_sbo = g_tc_swap;
+    a.act = d->act; a.slope = d->slope; a.three = three; a.swap_lbo_sbo = g_tc_swap & 1; a.swz = g_tc_swz;
     signed char tix[TC_MAX_TAPS];
     for (int ky = 0; ky < d->kh; ++ky)
         for (int kx = 0; kx < d->kw; ++kx) {
@@ -430,7 +440,7 @@ int tc_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const floa
             a.Hc = (d->Hi - py + s - 1) / s; a.Wc = (d->Wi - px + s - 1) / s;
             a.out_stride = s; a.out_oy = py; a.out_ox = px; a.in_stride = 1;
             a.M = d->B * a.Hc * a.Wc;
-            a.act = d->act; a.slope = d->slope; a.three = three; a.swap_lbo_sbo = g_tc_swap;
+            a.act = d->act; a.slope = d->slope; a.three = three; a.swap_lbo_sbo = g_tc_swap & 1; a.swz = g_tc_swz;
             signed char tix[TC_MAX_TAPS];
             int nt = 0;
             for (int ky = 0; ky < d->kh; ++ky) {
@@ -451,7 +461,7 @@ int tc_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const floa
     return CCB_OK;
 }
 
-void tc_set_debug_swap(int v) { g_tc_swap = v; }
+void tc_set_debug_swap(int v) { g_tc_swap = v & 1; g_tc_swz = (v >> 1) & 1; }
 
 }  // namespace ccb
 

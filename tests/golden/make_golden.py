@@ -211,7 +211,8 @@ def load_ref(mod, params):
 
 def gen_nets():
     d = {}
-    B, H, W = 2, 32, 64          # DispResNet6 / PoseNetB6 (any size works: crop_like)
+    B, H, W = 2, 64, 128         # DispResNet6 / PoseNetB6 (smaller inputs make the deepest BatchNorms, which see
+                                 # only B*1*1 values, ill-conditioned: fp32 summation order then changes grads by %)
     tgt, refs = synth.frames(B, H, W, seed=40)
     # DispResNet6
     P = onets.disp_params()

@@ -67,6 +67,42 @@ def case_conv_shapes(device, big=False):
             assert_close(a_, b_, TOL, tag + ' ' + nm)
 
 
+def case_conv_tc(device):
+    """tcgen05 path (3xTF32 = fp32 parity, and single TF32) against torch fp64 on real layer shapes;
+    GPU only (the simulator has no tensor cores)."""
+    from cc_b200 import _lib
+    g = torch.Generator().manual_seed(7)
+    shapes = [(2, 32, 16, 24, 64, 3, 1, 1), (2, 17, 13, 19, 40, 3, 2, 1), (4, 128, 32, 104, 128, 3, 1, 1),
+              (4, 32, 64, 208, 32, 7, 1, 3), (4, 65, 32, 104, 32, 1, 1, 0), (2, 256, 16, 52, 160, 3, 1, 1)]
+    saved = cnn.CONV_IMPL
+    try:
+        for (B, Ci, H, W, Co, k, s, p) in shapes:
+            x = torch.randn(B, Ci, H, W, generator=g).to(device).requires_grad_(True)
+            w = (torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5).to(device).requires_grad_(True)
+            b = torch.randn(Co, generator=g).to(device)
+            zd = F.leaky_relu(F.conv2d(x.double(), w.double(), b.double(), s, p), 0.2)
+            wt = _wts(zd.shape, 5, device)
+            gd = torch.autograd.grad((zd * wt.double()).sum(), [x])[0]
+            for impl, tol in ((_lib.IMPL_TC, 2e-5), (_lib.IMPL_TC_TF32, 3e-3)):
+                cnn.CONV_IMPL = impl
+                y = cnn.conv2d(x, w, b, None, s, p, 'leaky', 0.2)
+                assert_close(y, zd, tol, f'tc impl {impl} fprop {Ci}->{Co} k{k} s{s}')
+                gx = torch.autograd.grad((y * wt).sum(), [x])[0]      # dgrad on the tensor cores
+                assert_close(gx, gd, tol, f'tc impl {impl} dgrad {Ci}->{Co} k{k} s{s}')
+        # ConvTranspose2d forward == strided dgrad parity classes
+        x = torch.randn(2, 96, 16, 52, generator=g).to(device)
+        w = (torch.randn(96, 32, 4, 4, generator=g) * 0.05).to(device)
+        b = torch.randn(32, generator=g).to(device)
+        zd = F.relu(F.conv_transpose2d(x.double(), w.double(), b.double(), 2, 1))
+        cnn.CONV_IMPL = _lib.IMPL_TC
+        assert_close(cnn.conv_transpose2d(x, w, b, 2, 1, 0, 'relu'), zd, 2e-5, 'tc convT k4 s2')
+        w3 = (torch.randn(96, 32, 3, 3, generator=g) * 0.05).to(device)
+        zd = F.relu(F.conv_transpose2d(x.double(), w3.double(), b.double(), 2, 1, 1))
+        assert_close(cnn.conv_transpose2d(x, w3, b, 2, 1, 1, 'relu'), zd, 2e-5, 'tc convT k3 s2 op1')
+    finally:
+        cnn.CONV_IMPL = saved
+
+
 def case_bn_upsample(device):
     g = torch.Generator().manual_seed(1)
     x = torch.randn(3, 6, 5, 7, generator=g).to(device).requires_grad_(True)
@@ -108,7 +144,7 @@ def _check_grads(g, prefix, names, pd, grads, tol):
 def case_disp_pose_golden(device):
     """DispResNet6 + PoseNetB6 modules (reference state_dict keys) vs fixtures from the reference nets."""
     g = golden('nets_small')
-    tgt, refs = synth.frames(2, 32, 64, seed=40)
+    tgt, refs = synth.frames(2, 64, 128, seed=40)
     tgt, refs = tgt.to(device), [r.to(device) for r in refs]
     net = _load(CM.DispResNet6(), ON.disp_params(), device)
     net.train()

@@ -79,3 +79,7 @@ def test_flat_adam():
 
 def test_train_step_cfg1_vs_oracle():
     SC.case_step_cfg1(torch.device('cuda:0'))
+
+
+def test_conv_tensor_core_path():
+    NC.case_conv_tc(torch.device('cuda:0'))

@@ -145,7 +145,7 @@ NTOL = 2e-5   # conv algorithm choice (mkldnn) may differ between module and fun
 
 def test_nets():
     g = golden('nets_small')
-    B, H, W = 2, 32, 64
+    B, H, W = 2, 64, 128
     tgt, refs = synth.frames(B, H, W, seed=40)
     wts = lambda shape, seed: torch.randn(shape, generator=torch.Generator().manual_seed(seed))
     P = N.clone_params(N.disp_params(), requires_grad=True)

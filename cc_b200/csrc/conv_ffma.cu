@@ -339,6 +339,9 @@ int tc_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float
 int tc_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const float* bias, const float* res, float* dx,
              float* work, long long work_floats, int three, cudaStream_t st);
 
+int tc_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw, float* work, long long work_floats,
+             int three, cudaStream_t st);
+
 // 0: FFMA, 1: tcgen05 3xTF32, 2: tcgen05 single TF32
 static int pick_impl(const ccb_conv_desc* d, int op) {
     switch (d->impl) {
@@ -422,6 +425,19 @@ extern "C" int ccb_conv2d_wgrad(const ccb_conv_desc* d, const float* x, const fl
     int rc = fill_conv(a, d);
     if (rc) return rc;
     CCB_REQUIRE(x && dy && dw, CCB_ERR_ARG, "conv2d_wgrad: null pointer");
+    {
+        int impl = pick_impl(d, CCB_CONV_WGRAD);
+        CCB_REQUIRE(impl >= 0, CCB_ERR_UNSUPPORTED, "conv2d_wgrad: shape not supported by the tensor-core path");
+        if (impl > 0) {
+            rc = tc_wgrad(d, x, dy, dw, work, work_floats, impl == 1, (cudaStream_t)stream);
+            if (rc) return rc;
+            if (db) {
+                CCB_LAUNCH(bias_grad_kernel, dim3(d->Co), dim3(256), 0, stream, dy, db, d->B, d->Co, d->Ho * d->Wo);
+                rc = check_launch("bias_grad");
+            }
+            return rc;
+        }
+    }
     a.x = x; a.dy = dy; a.out = dw; a.work = work; a.act = CCB_ACT_NONE;
     a.M = a.Ci * a.kh * a.kw; a.N = a.Co; a.K = a.B * a.Ho * a.Wo;
     rc = launch_gemm<MODE_WGRAD>(a, (long long)a.M * a.N, work_floats, (cudaStream_t)stream, "conv2d_wgrad");

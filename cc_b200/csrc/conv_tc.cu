@@ -169,11 +169,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
     const long long HWin = (long long)a.Hin * a.Win;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS / 2); mbar_init(&empty_bar[s], 1); }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, 128);
+    if (warp == 8) tmem_alloc(tmem_slot, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -181,7 +181,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
 
     if (warp < 8) {
         // ===================== producers =====================
-        const int r = tid & 127, half = tid >> 7;
+        // Two groups of 4 warps fill alternating stages, so one group's global-load latency overlaps the
+        // other group's convert + shared-memory store phase.  Within a group: thread == tile row.
+        const int grp = warp >> 2, r = tid & 127;
         const int m = m0 + r;
         const bool mvalid = m < a.M;
         int b = 0, oy = 0, ox = 0;
@@ -196,56 +198,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
         const int iy0 = oy * a.in_stride, ix0 = ox * a.in_stride;
         const int cpt = a.cpad >> 2;                 // chunks per tap
         const int nchunks = a.ntaps * cpt;           // real chunks; the rest of Kp is zero padding
-        for (int it = 0; it < ktiles; ++it) {
+        for (int it = grp; it < ktiles; it += 2) {
             const int s = it % TC_STAGES;
+            // ---- A: the 8 chunks (32 floats) of this thread's pixel row; tap/channel walk incrementally
+            float av[TC_KC][4];
+            int q = it * TC_KC;
+            int tap = q / cpt, c4 = q - tap * cpt;
+#pragma unroll
+            for (int c = 0; c < TC_KC; ++c) {
+                av[c][0] = av[c][1] = av[c][2] = av[c][3] = 0.f;
+                if (mvalid && q < nchunks) {
+                    const int iy = iy0 + a.off_y[tap], ix = ix0 + a.off_x[tap];
+                    if (iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) {
+                        const float* p = xb + (long long)(c4 * 4) * HWin + (iy * a.Win + ix);
+                        const int nv = a.Cin - c4 * 4;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < nv) av[c][j] = __ldg(p + j * HWin);
+                    }
+                }
+                ++q;
+                if (++c4 == cpt) { c4 = 0; ++tap; }
+            }
+            // ---- B: 8 float4 of the prepared weight tile (pairs of threads cover one 32-byte sector)
+            float4 bv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int idx = r + j * 128;                      // 0 .. 1023
+                const int c = ((idx >> 8) << 1) | (idx & 1);
+                const int n = (idx >> 1) & 127;
+                bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n < ntile) bv[j] = __ldg((const float4*)(a.wp + (long long)(n0 + n) * a.Kp + it * (TC_KC * 4) + c * 4));
+            }
             if (it >= TC_STAGES) mbar_wait(&empty_bar[s], ((it / TC_STAGES) - 1) & 1);
             unsigned char* st = smem + s * TC_STAGE_BYTES;
             float4* a_hi = (float4*)st;
             float4* a_lo = (float4*)(st + TC_TILE_BYTES);
             float4* b_hi = (float4*)(st + 2 * TC_TILE_BYTES);
             float4* b_lo = (float4*)(st + 3 * TC_TILE_BYTES);
-            // ---- A: 4 chunks of this thread's pixel row
-            float av[4][4];
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int c = half * 4 + cc;
-                const int q = it * TC_KC + c;
-                av[cc][0] = av[cc][1] = av[cc][2] = av[cc][3] = 0.f;
-                if (mvalid && q < nchunks) {
-                    const int tap = q / cpt, c4 = q - tap * cpt;
-                    const int iy = iy0 + a.off_y[tap], ix = ix0 + a.off_x[tap];
-                    if (iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) {
-                        const float* p = xb + (long long)(c4 * 4) * HWin + (long long)iy * a.Win + ix;
-                        const int nv = a.Cin - c4 * 4;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j < nv) av[cc][j] = __ldg(p + j * HWin);
-                    }
-                }
-            }
-            // ---- B: 4 float4 of the prepared weight tile
-            float4 bv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int idx = tid + j * TC_PRODUCERS;           // 0 .. 1023
-                const int c = ((idx >> 8) << 1) | (idx & 1);      // idx / (2*128) * 2 + (idx & 1)
-                const int n = (idx >> 1) & 127;
-                bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n < ntile) bv[j] = __ldg((const float4*)(a.wp + (long long)(n0 + n) * a.Kp + it * (TC_KC * 4) + c * 4));
-            }
             // ---- split + store
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int c = half * 4 + cc;
+            for (int c = 0; c < TC_KC; ++c) {
                 float4 h, l;
-                h.x = tf32_hi(av[cc][0]); h.y = tf32_hi(av[cc][1]); h.z = tf32_hi(av[cc][2]); h.w = tf32_hi(av[cc][3]);
-                l.x = av[cc][0] - h.x; l.y = av[cc][1] - h.y; l.z = av[cc][2] - h.z; l.w = av[cc][3] - h.w;
+                h.x = tf32_hi(av[c][0]); h.y = tf32_hi(av[c][1]); h.z = tf32_hi(av[c][2]); h.w = tf32_hi(av[c][3]);
+                l.x = av[c][0] - h.x; l.y = av[c][1] - h.y; l.z = av[c][2] - h.z; l.w = av[c][3] - h.w;
                 a_hi[tile_idx(r, c, a.swz)] = h;
                 a_lo[tile_idx(r, c, a.swz)] = l;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int idx = tid + j * TC_PRODUCERS;
+            for (int j = 0; j < 8; ++j) {
+                const int idx = r + j * 128;
                 const int c = ((idx >> 8) << 1) | (idx & 1);
                 const int n = (idx >> 1) & 127;
                 float4 h, l;
@@ -276,6 +278,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
         for (int cg = colhalf; cg * 16 < umma_n; cg += 2) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(cg * 16), v);
+            if (a.three) {
+                float vl[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + 128u + (uint32_t)(cg * 16), vl);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += vl[j];
+            }
             if (evalid) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -313,10 +321,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
                     const uint64_t al = make_desc(base + TC_TILE_BYTES + koff, lbo, sbo, ltype);
                     const uint64_t bh = make_desc(base + 2 * TC_TILE_BYTES + koff, lbo, sbo, ltype);
                     const uint64_t bl = make_desc(base + 3 * TC_TILE_BYTES + koff, lbo, sbo, ltype);
+                    // hi*hi goes to columns [0,128); the two small cross terms to [128,256): the tensor core
+                    // truncates on every accumulate, so keeping the small terms out of the big accumulator
+                    // (and summing them in fp32 in the epilogue) cuts the accumulated bias ~3x
                     umma_tf32(tmem_base, ah, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
                     if (a.three) {
-                        umma_tf32(tmem_base, al, bh, idesc, 1u);
-                        umma_tf32(tmem_base, ah, bl, idesc, 1u);
+                        umma_tf32(tmem_base + 128u, al, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                        umma_tf32(tmem_base + 128u, ah, bl, idesc, 1u);
                     }
                 }
                 umma_commit(&empty_bar[s]);                 // frees the stage when these MMAs have read it
@@ -329,7 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 128);
+        tmem_dealloc(tmem_base, 256);
     }
 }
 
@@ -381,13 +392,209 @@ static int launch_tc(TcArgs& a, const float* w, int mode, int N, int Cc, int KK,
     return check_launch("conv_tc");
 }
 
+// ================================================================================================
+// WGRAD on the tensor cores:  D[m=(tap,ci)][n=co] = sum_{k=pixel} X_im2col[m][k] * dY[n][k]
+// Both operands are K(=pixel)-contiguous in NCHW, so producers walk along K: 8 consecutive threads
+// load the 8 16-byte chunks (32 consecutive output pixels) of one row -> coalesced global loads, and
+// with the SWIZZLE_128B operand layout their shared-memory stores are conflict-free.
+// Split-K over pixel ranges (grid.z) with a deterministic two-stage reduce.
+struct TcWgradArgs {
+    const float* x;      // [B,Ci,Hi,Wi]
+    const float* dy;     // [B,Co,Ho,Wo]
+    float* out;          // dw [Co,Ci,kh,kw]  or  work[splits][Co*Ci*kh*kw]
+    int B, Ci, Hi, Wi, Co, Ho, Wo, kh, kw, stride, pad;
+    int cpad, Mtot;      // channels padded to 4; Mtot = kh*kw*cpad rows
+    int P;               // B*Ho*Wo pixels (Wo % 4 == 0)
+    int stages, per_split, splits;
+    int three, swz, swap_lbo_sbo;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWgradArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + TC_STAGES;
+    uint64_t* accum_bar = empty_bar + TC_STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * TC_M, n0 = blockIdx.y * TC_NMAX;
+    const int ntile = min(TC_NMAX, a.Co - n0);
+    const int umma_n = (ntile + 15) & ~15;
+    const int st_beg = blockIdx.z * a.per_split, st_end = min(a.stages, st_beg + a.per_split);
+    const int nst = st_end - st_beg;          // >= 1 by construction
+    const int KK = a.kh * a.kw;
+    const int HWo = a.Ho * a.Wo, HWi = a.Hi * a.Wi;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        const int c = tid & 7, rbase = tid >> 3;      // chunk along K, rows rbase + 32 j
+        // decode this thread's 4 A rows (tap, ci) once
+        int a_ci[4], a_ky[4], a_kx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int m = m0 + rbase + 32 * j;
+            a_ci[j] = -1; a_ky[j] = a_kx[j] = 0;
+            if (m < a.Mtot) {
+                int tap = m / a.cpad, ci = m - tap * a.cpad;
+                if (ci < a.Ci) { a_ci[j] = ci; a_ky[j] = tap / a.kw; a_kx[j] = tap - a_ky[j] * a.kw; }
+            }
+        }
+        for (int it = 0; it < nst; ++it) {
+            const int s = it % TC_STAGES;
+            if (it >= TC_STAGES) mbar_wait(&empty_bar[s], ((it / TC_STAGES) - 1) & 1);
+            unsigned char* st = smem + s * TC_STAGE_BYTES;
+            float4* a_hi = (float4*)st;
+            float4* a_lo = (float4*)(st + TC_TILE_BYTES);
+            float4* b_hi = (float4*)(st + 2 * TC_TILE_BYTES);
+            float4* b_lo = (float4*)(st + 3 * TC_TILE_BYTES);
+            const int p0 = ((st_beg + it) * TC_KC + c) * 4;       // first of this chunk's 4 pixels
+            const bool pvalid = p0 < a.P;
+            int b = 0, oy = 0, ox0 = 0;
+            if (pvalid) {
+                b = p0 / HWo;
+                int rem = p0 - b * HWo;
+                oy = rem / a.Wo;
+                ox0 = rem - oy * a.Wo;
+            }
+            float av[4][4];
+            float4 bv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                av[j][0] = av[j][1] = av[j][2] = av[j][3] = 0.f;
+                if (pvalid && a_ci[j] >= 0) {
+                    const int iy = oy * a.stride - a.pad + a_ky[j];
+                    if (iy >= 0 && iy < a.Hi) {
+                        const float* px = a.x + ((long long)b * a.Ci + a_ci[j]) * HWi + iy * a.Wi;
+                        const int ix0 = ox0 * a.stride - a.pad + a_kx[j];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int ix = ix0 + e * a.stride;
+                            if (ix >= 0 && ix < a.Wi) av[j][e] = __ldg(px + ix);
+                        }
+                    }
+                }
+                bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int n = rbase + 32 * j;
+                if (pvalid && n < ntile)
+                    bv[j] = __ldg((const float4*)(a.dy + ((long long)b * a.Co + n0 + n) * HWo + oy * a.Wo + ox0));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = rbase + 32 * j;
+                float4 h, l;
+                h.x = tf32_hi(av[j][0]); h.y = tf32_hi(av[j][1]); h.z = tf32_hi(av[j][2]); h.w = tf32_hi(av[j][3]);
+                l.x = av[j][0] - h.x; l.y = av[j][1] - h.y; l.z = av[j][2] - h.z; l.w = av[j][3] - h.w;
+                a_hi[tile_idx(r, c, a.swz)] = h;
+                a_lo[tile_idx(r, c, a.swz)] = l;
+                h.x = tf32_hi(bv[j].x); h.y = tf32_hi(bv[j].y); h.z = tf32_hi(bv[j].z); h.w = tf32_hi(bv[j].w);
+                l.x = bv[j].x - h.x; l.y = bv[j].y - h.y; l.z = bv[j].z - h.z; l.w = bv[j].w - h.w;
+                b_hi[tile_idx(r, c, a.swz)] = h;
+                b_lo[tile_idx(r, c, a.swz)] = l;
+            }
+            fence_proxy_async();
+            mbar_arrive(&full_bar[s]);
+        }
+        // ---- epilogue: lane == row m = (tap, ci); columns == co
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int q4 = warp & 3, colhalf = warp >> 2;
+        const int em = m0 + q4 * 32 + lane;
+        int eci = -1, etap = 0;
+        if (em < a.Mtot) {
+            etap = em / a.cpad;
+            int ci = em - etap * a.cpad;
+            if (ci < a.Ci) eci = ci;
+        }
+        float* outp = a.out + (long long)blockIdx.z * a.Co * a.Ci * KK;
+        for (int cg = colhalf; cg * 16 < umma_n; cg += 2) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(cg * 16), v);
+            if (a.three) {
+                float vl[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + 128u + (uint32_t)(cg * 16), vl);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += vl[j];
+            }
+            if (eci >= 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = cg * 16 + j;
+                    if (n < ntile) outp[((long long)(n0 + n) * a.Ci + eci) * KK + etap] = v[j];
+                }
+            }
+        }
+        tc_fence_before();
+    } else {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+        uint32_t lbo = a.swz ? 16u : (uint32_t)(TC_M * 16);
+        uint32_t sbo = a.swz ? 1024u : 128u;
+        if (a.swap_lbo_sbo) { uint32_t t = lbo; lbo = sbo; sbo = t; }
+        const uint32_t ltype = a.swz ? 2u : 0u;
+        const uint32_t kstep_bytes = a.swz ? 32u : 2u * (uint32_t)(TC_M * 16);
+        for (int it = 0; it < nst; ++it) {
+            const int s = it % TC_STAGES;
+            mbar_wait(&full_bar[s], (it / TC_STAGES) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t base = smem_u32(smem + s * TC_STAGE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < TC_KC / 2; ++ks) {
+                    const uint32_t koff = (uint32_t)ks * kstep_bytes;
+                    const uint64_t ah = make_desc(base + koff, lbo, sbo, ltype);
+                    const uint64_t al = make_desc(base + TC_TILE_BYTES + koff, lbo, sbo, ltype);
+                    const uint64_t bh = make_desc(base + 2 * TC_TILE_BYTES + koff, lbo, sbo, ltype);
+                    const uint64_t bl = make_desc(base + 3 * TC_TILE_BYTES + koff, lbo, sbo, ltype);
+                    // hi*hi goes to columns [0,128); the two small cross terms to [128,256): the tensor core
+                    // truncates on every accumulate, so keeping the small terms out of the big accumulator
+                    // (and summing them in fp32 in the epilogue) cuts the accumulated bias ~3x
+                    umma_tf32(tmem_base, ah, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                    if (a.three) {
+                        umma_tf32(tmem_base + 128u, al, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                        umma_tf32(tmem_base + 128u, ah, bl, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+                if (it == nst - 1) umma_commit(accum_bar);
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// out[i] = sum_s work[s][i]
+__global__ void __launch_bounds__(256) tc_splitk_sum_kernel(const float* __restrict__ work, float* __restrict__ out,
+                                                            long long numel, int splits) {
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= numel) return;
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += __ldg(work + (long long)s * numel + i);
+    out[i] = v;
+}
+
 static int g_tc_swap = 0;
-static int g_tc_swz = 0;
+static int g_tc_swz = 1;     // SWIZZLE_128B by default; the no-swizzle layout stays selectable for the probe
 
 // Shape gate: which problems take the tensor-core path under CCB_CONV_IMPL_AUTO
 bool tc_supported(const ccb_conv_desc* d, int op) {
     if (d->kh != d->kw || d->kh * d->kw > TC_MAX_TAPS) return false;
-    if (op == CCB_CONV_WGRAD) return false;
+    if (op == CCB_CONV_WGRAD) return (d->Wo % 4 == 0);      // 16-byte pixel chunks must not straddle rows
     return true;
 }
 bool tc_profitable(const ccb_conv_desc* d, int op) {
@@ -395,10 +602,30 @@ bool tc_profitable(const ccb_conv_desc* d, int op) {
     long long M = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Ho * d->Wo : (long long)d->B * d->Hi * d->Wi;
     int N = (op == CCB_CONV_FPROP) ? d->Co : d->Ci;
     int Cc = (op == CCB_CONV_FPROP) ? d->Ci : d->Co;
-    return M >= 1024 && N >= 16 && Cc * d->kh * d->kw >= 32;
+    (void)N;
+    return M >= 1024 && Cc * d->kh * d->kw >= 16;
+}
+
+static int wgrad_splits(const ccb_conv_desc* d, int& stages, int& per_split) {
+    const int cpad = roundup(d->Ci, 4);
+    const long long P = (long long)d->B * d->Ho * d->Wo;
+    stages = (int)((P + 31) / 32);
+    const int tiles = cdiv(d->kh * d->kw * cpad, TC_M) * cdiv(d->Co, TC_NMAX);
+    int splits = cdiv(2 * 148, tiles);
+    if (splits > stages / 4) splits = stages / 4;
+    if (splits > 32) splits = 32;
+    if (splits < 1) splits = 1;
+    per_split = cdiv(stages, splits);
+    splits = cdiv(stages, per_split);          // no empty split
+    return splits;
 }
 
 long long tc_workspace_floats(const ccb_conv_desc* d, int op) {
+    if (op == CCB_CONV_WGRAD) {
+        int stages, per;
+        int splits = wgrad_splits(d, stages, per);
+        return splits > 1 ? (long long)splits * d->Co * d->Ci * d->kh * d->kw : 0;
+    }
     int N = (op == CCB_CONV_FPROP) ? d->Co : d->Ci;
     int Cc = (op == CCB_CONV_FPROP) ? d->Ci : d->Co;
     return (long long)N * roundup(d->kh * d->kw * roundup(Cc, 4), 32);
@@ -461,7 +688,35 @@ int tc_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const floa
     return CCB_OK;
 }
 
-void tc_set_debug_swap(int v) { g_tc_swap = v & 1; g_tc_swz = (v >> 1) & 1; }
+int tc_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw, float* work, long long work_floats,
+             int three, cudaStream_t st) {
+    TcWgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.dy = dy;
+    a.B = d->B; a.Ci = d->Ci; a.Hi = d->Hi; a.Wi = d->Wi; a.Co = d->Co; a.Ho = d->Ho; a.Wo = d->Wo;
+    a.kh = d->kh; a.kw = d->kw; a.stride = d->stride; a.pad = d->pad;
+    a.cpad = roundup(d->Ci, 4);
+    a.Mtot = d->kh * d->kw * a.cpad;
+    a.P = d->B * d->Ho * d->Wo;
+    a.splits = wgrad_splits(d, a.stages, a.per_split);
+    a.three = three; a.swz = g_tc_swz; a.swap_lbo_sbo = g_tc_swap & 1;
+    const long long numel = (long long)d->Co * d->Ci * d->kh * d->kw;
+    if (a.splits > 1) {
+        CCB_REQUIRE(work && (long long)a.splits * numel <= work_floats, CCB_ERR_ARG, "conv_tc wgrad: workspace too small");
+        a.out = work;
+    } else {
+        a.out = dw;
+    }
+    { static bool once = false; if (!once) { cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); once = true; } }
+    dim3 grid(cdiv(a.Mtot, TC_M), cdiv(d->Co, TC_NMAX), a.splits);
+    CCB_LAUNCH(conv_tc_wgrad_kernel, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, a);
+    int rc = check_launch("conv_tc_wgrad");
+    if (rc || a.splits == 1) return rc;
+    CCB_LAUNCH(tc_splitk_sum_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), 0, st, (const float*)work, dw, numel, a.splits);
+    return check_launch("conv_tc_wgrad_reduce");
+}
+
+void tc_set_debug_swap(int v) { g_tc_swap = v & 1; g_tc_swz = (v & 4) ? 0 : 1; }
 
 }  // namespace ccb
 
@@ -477,6 +732,9 @@ int tc_fprop(const ccb_conv_desc*, const float*, const float*, const float*, con
              cudaStream_t) { return CCB_ERR_UNSUPPORTED; }
 int tc_dgrad(const ccb_conv_desc*, const float*, const float*, const float*, const float*, float*, float*, long long, int,
              cudaStream_t) { return CCB_ERR_UNSUPPORTED; }
+int tc_wgrad(const ccb_conv_desc*, const float*, const float*, float*, float*, long long, int, cudaStream_t) {
+    return CCB_ERR_UNSUPPORTED;
+}
 }  // namespace ccb
 extern "C" void ccb_debug_tc_swap_strides(int) {}
 

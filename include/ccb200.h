@@ -225,8 +225,9 @@ int ccb_conv2d_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, fl
 int ccb_act_bwd(const float* dy, const float* y, float* dz, long long numel, int act, float slope,
                 ccb_stream_t stream);
 int ccb_bias_grad(const float* dy, float* db, int B, int C, int plane, ccb_stream_t stream);
-/* bring-up aid (layout probe): bit 0 swaps the LBO/SBO strides of the UMMA shared-memory descriptors,
- * bit 1 selects the K-major SWIZZLE_128B operand layout instead of the no-swizzle one */
+/* bring-up aid (layout probe): bit 0 swaps the LBO/SBO strides of the UMMA shared-memory descriptors
+ * (must produce wrong results), bit 2 selects the K-major no-swizzle operand layout instead of the
+ * default SWIZZLE_128B one (must produce identical results) */
 void ccb_debug_tc_swap_strides(int swap);
 
 /* Back2Future operators (models/back2future.py).

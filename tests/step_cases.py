@@ -38,8 +38,10 @@ def _oracle_params_as_state_dicts(P):
     return {n: {k: v.detach().clone() for k, v in d.items()} for n, d in P.items()}
 
 
-def case_step_cfg1(device, B=2, H=128, W=416, steps=2):
-    """cfg1 (BASELINE.json configs[1] at reduced batch/size): loss and gradients of step 1, loss of step 2."""
+def case_step_cfg1(device, B=2, H=128, W=416, steps=2, gtol=4e-3):
+    """cfg1 (BASELINE.json configs[1] at reduced batch/size): loss and gradients of step 1, loss of step 2.
+    gtol: 4e-3 with the exact-fp32 FFMA convolutions (measured 1.3e-3: fp32 noise through ~50 layers incl.
+    batch-stat BNs over <= 8 values); the tensor-core (3xTF32) path is held to 5e-2 on the same gradients."""
     tgt, refs = synth.frames(B, H, W, seed=50)
     K, Kinv = synth.intrinsics(B, H, W)
     P = OS.make_params('cfg1')
@@ -59,7 +61,7 @@ def case_step_cfg1(device, B=2, H=128, W=416, steps=2):
                     if name in ('conv1.0.weight', 'conv1.2.weight', 'conv4.0.conv1.weight', 'iconv2.0.conv2.weight',
                                 'predict_disp1.0.weight', 'upconv3.0.weight', 'pose_pred.weight', 'conv7.0.downsample.1.weight'):
                         # fp32 noise accumulated through ~50 layers incl. batch-stat BNs over <= 8 values: measured 1.3e-3
-                        assert_close(p._ccb_grad, g, 4e-3, f'{net}.{name} grad')
+                        assert_close(p._ccb_grad, g, gtol, f'{net}.{name} grad')
     return tr
 
 

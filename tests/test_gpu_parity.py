@@ -78,7 +78,15 @@ def test_flat_adam():
 
 
 def test_train_step_cfg1_vs_oracle():
-    SC.case_step_cfg1(torch.device('cuda:0'))
+    from cc_b200 import nn as cnn, _lib
+    saved = cnn.CONV_IMPL
+    try:
+        cnn.CONV_IMPL = _lib.IMPL_FFMA
+        SC.case_step_cfg1(torch.device('cuda:0'), gtol=4e-3)
+        cnn.CONV_IMPL = _lib.IMPL_AUTO
+        SC.case_step_cfg1(torch.device('cuda:0'), gtol=5e-2)
+    finally:
+        cnn.CONV_IMPL = saved
 
 
 def test_conv_tensor_core_path():

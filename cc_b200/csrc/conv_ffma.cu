@@ -276,6 +276,49 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
     if (threadIdx.x == 0) db[c] = v[0];
 }
 
+// parallel variant for few channels x large planes: grid (C, nsplit) partials, then a per-channel merge
+constexpr int BG_CHUNK = 16384;
+__global__ void __launch_bounds__(256) bias_grad_partial_kernel(const float* __restrict__ dy, float* __restrict__ part, int B,
+                                                                int C, int plane, int nsplit) {
+    __shared__ float s_red[32];
+    const int c = blockIdx.x, sp = blockIdx.y;
+    const long long per = (long long)B * plane;
+    const long long beg = (long long)sp * BG_CHUNK, end = min(per, beg + (long long)BG_CHUNK);
+    float v[1] = {0.f};
+    for (long long i = beg + threadIdx.x; i < end; i += 256) {
+        int b = (int)(i / plane), o = (int)(i - (long long)b * plane);
+        v[0] += __ldg(dy + ((long long)b * C + c) * plane + o);
+    }
+    block_sum<1>(v, s_red);
+    if (threadIdx.x == 0) part[(long long)c * nsplit + sp] = v[0];
+}
+__global__ void bias_grad_merge_kernel(const float* __restrict__ part, float* __restrict__ db, int C, int nsplit) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float a = 0.f;
+    for (int s = 0; s < nsplit; ++s) a += part[(long long)c * nsplit + s];
+    db[c] = a;
+}
+
+static int launch_bias_grad(const float* dy, float* db, int B, int C, int plane, float* work, long long work_floats,
+                            cudaStream_t st) {
+    const long long per = (long long)B * plane;
+    const int nsplit = (int)((per + BG_CHUNK - 1) / BG_CHUNK);
+    if (nsplit > 1 && work && (long long)C * nsplit <= work_floats) {
+        CCB_LAUNCH(bias_grad_partial_kernel, dim3(C, nsplit), dim3(256), 0, st, dy, work, B, C, plane, nsplit);
+        CCB_LAUNCH(bias_grad_merge_kernel, dim3(cdiv(C, 128)), dim3(128), 0, st, (const float*)work, db, C, nsplit);
+    } else {
+        CCB_LAUNCH(bias_grad_kernel, dim3(C), dim3(256), 0, st, dy, db, B, C, plane);
+    }
+    return check_launch("bias_grad");
+}
+
+void launch_splitk_reduce(const float* work, float* out, const float* bias, const float* res, long long numel, int splits,
+                          int plane, int C, int act, float slope, cudaStream_t st) {
+    CCB_LAUNCH(splitk_reduce_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), 0, st, work, out, bias, res, numel, splits,
+               plane, C, act, slope);
+}
+
 // ------------------------------------------------------------------------------------------------
 static int pick_splits(int tiles, int ktiles, int max_splits) {
     const int target = 148 * 4;
@@ -346,8 +389,9 @@ int tc_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw,
 static int pick_impl(const ccb_conv_desc* d, int op) {
     switch (d->impl) {
         case CCB_CONV_IMPL_FFMA: return 0;
-        case CCB_CONV_IMPL_TC: return tc_supported(d, op) ? 1 : -1;
-        case CCB_CONV_IMPL_TC_TF32: return tc_supported(d, op) ? 2 : -1;
+        // forcing the tensor-core path falls back to FFMA only for shapes it cannot express at all
+        case CCB_CONV_IMPL_TC: return tc_supported(d, op) ? 1 : 0;
+        case CCB_CONV_IMPL_TC_TF32: return tc_supported(d, op) ? 2 : 0;
         default: return tc_profitable(d, op) ? 1 : 0;
     }
 }
@@ -358,7 +402,11 @@ using namespace ccb;
 
 extern "C" long long ccb_conv_workspace_floats(const ccb_conv_desc* d, int op) {
     if (!d) return -1;
-    if (d->impl != CCB_CONV_IMPL_FFMA && tc_supported(d, op) && pick_impl(d, op) > 0) return tc_workspace_floats(d, op);
+    const long long bias_need = (op == CCB_CONV_WGRAD) ? (long long)d->Co * (((long long)d->B * d->Ho * d->Wo + BG_CHUNK - 1) / BG_CHUNK) : 0;
+    if (d->impl != CCB_CONV_IMPL_FFMA && tc_supported(d, op) && pick_impl(d, op) > 0) {
+        long long t = tc_workspace_floats(d, op);
+        return t > bias_need ? t : bias_need;
+    }
     long long numel = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Co * d->Ho * d->Wo
                     : (op == CCB_CONV_DGRAD) ? (long long)d->B * d->Ci * d->Hi * d->Wi
                                              : (long long)d->Co * d->Ci * d->kh * d->kw;
@@ -366,7 +414,8 @@ extern "C" long long ccb_conv_workspace_floats(const ccb_conv_desc* d, int op) {
     long long cap = 16ll * 1024 * 1024;
     long long want = numel * 16;
     if (want > cap) want = (cap / numel) * numel;
-    return want < numel ? 0 : want;
+    if (want < numel) want = 0;
+    return want > bias_need ? want : bias_need;
 }
 
 extern "C" int ccb_conv2d_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float* bias,
@@ -431,10 +480,7 @@ extern "C" int ccb_conv2d_wgrad(const ccb_conv_desc* d, const float* x, const fl
         if (impl > 0) {
             rc = tc_wgrad(d, x, dy, dw, work, work_floats, impl == 1, (cudaStream_t)stream);
             if (rc) return rc;
-            if (db) {
-                CCB_LAUNCH(bias_grad_kernel, dim3(d->Co), dim3(256), 0, stream, dy, db, d->B, d->Co, d->Ho * d->Wo);
-                rc = check_launch("bias_grad");
-            }
+            if (db) rc = launch_bias_grad(dy, db, d->B, d->Co, d->Ho * d->Wo, work, work_floats, (cudaStream_t)stream);
             return rc;
         }
     }
@@ -442,10 +488,7 @@ extern "C" int ccb_conv2d_wgrad(const ccb_conv_desc* d, const float* x, const fl
     a.M = a.Ci * a.kh * a.kw; a.N = a.Co; a.K = a.B * a.Ho * a.Wo;
     rc = launch_gemm<MODE_WGRAD>(a, (long long)a.M * a.N, work_floats, (cudaStream_t)stream, "conv2d_wgrad");
     if (rc) return rc;
-    if (db) {
-        CCB_LAUNCH(bias_grad_kernel, dim3(a.Co), dim3(256), 0, stream, dy, db, a.B, a.Co, a.Ho * a.Wo);
-        rc = check_launch("bias_grad");
-    }
+    if (db) rc = launch_bias_grad(dy, db, a.B, a.Co, a.Ho * a.Wo, work, work_floats, (cudaStream_t)stream);
     return rc;
 }
 
@@ -459,6 +502,5 @@ extern "C" int ccb_act_bwd(const float* dy, const float* y, float* dz, long long
 
 extern "C" int ccb_bias_grad(const float* dy, float* db, int B, int C, int plane, ccb_stream_t stream) {
     CCB_REQUIRE(dy && db, CCB_ERR_ARG, "bias_grad: null pointer");
-    CCB_LAUNCH(bias_grad_kernel, dim3(C), dim3(256), 0, stream, dy, db, B, C, plane);
-    return check_launch("bias_grad");
+    return launch_bias_grad(dy, db, B, C, plane, nullptr, 0, (cudaStream_t)stream);
 }

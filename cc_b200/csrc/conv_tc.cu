@@ -50,6 +50,10 @@ struct TcArgs {
     int three;             // 1: 3xTF32, 0: single TF32
     int swap_lbo_sbo;      // debug: swap the descriptor strides (layout probe)
     int swz;               // 0: K-major no-swizzle [chunk][row][16B]; 1: K-major SWIZZLE_128B [row][128B], chunk ^= row&7
+    int splits, kt_per_split;          // split-K over k-tiles (grid.z); partials go to `partial`
+    float* partial;                    // [splits][numel(out)] raw accumulators (bias/res/act applied by the reduce kernel)
+    long long out_numel;
+    int stages, b_tile_bytes;          // pipeline depth and bytes of one B operand copy (N-tile dependent)
     signed char off_y[TC_MAX_TAPS], off_x[TC_MAX_TAPS];
 };
 
@@ -153,11 +157,13 @@ constexpr int TC_TILE_BYTES = TC_KC * TC_M * 16;                   // one operan
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                  // A hi, A lo, B hi, B lo
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 2048;   // + barriers / tmem slot / alignment slack
 
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms are 1 KB
-    uint64_t* full_bar = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + TC_STAGES;
+    const int NST = a.stages;
+    const int stage_bytes = 2 * TC_TILE_BYTES + 2 * a.b_tile_bytes;     // A hi, A lo, B hi, B lo
+    uint64_t* full_bar = (uint64_t*)(smem + NST * stage_bytes);
+    uint64_t* empty_bar = full_bar + TC_STAGES;      // (barrier arrays sized for the maximum depth)
     uint64_t* accum_bar = empty_bar + TC_STAGES;
     uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
 
@@ -165,11 +171,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
     const int m0 = blockIdx.x * TC_M, n0 = blockIdx.y * TC_NMAX;
     const int ntile = min(TC_NMAX, a.Ntot - n0);
     const int umma_n = (ntile + 15) & ~15;
-    const int ktiles = a.Kp / (TC_KC * 4);
+    const int ktiles_all = a.Kp / (TC_KC * 4);
+    const int kt_beg = blockIdx.z * a.kt_per_split;
+    const int ktiles = max(0, min(ktiles_all, kt_beg + a.kt_per_split) - kt_beg);   // k-tiles of this split
     const long long HWin = (long long)a.Hin * a.Win;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS / 2); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS / 2); mbar_init(&empty_bar[s], 1); }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
@@ -199,10 +207,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
         const int cpt = a.cpad >> 2;                 // chunks per tap
         const int nchunks = a.ntaps * cpt;           // real chunks; the rest of Kp is zero padding
         for (int it = grp; it < ktiles; it += 2) {
-            const int s = it % TC_STAGES;
+            const int s = it % NST;
+            const int kt = kt_beg + it;                   // global k-tile
             // ---- A: the 8 chunks (32 floats) of this thread's pixel row; tap/channel walk incrementally
             float av[TC_KC][4];
-            int q = it * TC_KC;
+            int q = kt * TC_KC;
             int tap = q / cpt, c4 = q - tap * cpt;
 #pragma unroll
             for (int c = 0; c < TC_KC; ++c) {
@@ -228,14 +237,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
                 const int c = ((idx >> 8) << 1) | (idx & 1);
                 const int n = (idx >> 1) & 127;
                 bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n < ntile) bv[j] = __ldg((const float4*)(a.wp + (long long)(n0 + n) * a.Kp + it * (TC_KC * 4) + c * 4));
+                if (n < ntile) bv[j] = __ldg((const float4*)(a.wp + (long long)(n0 + n) * a.Kp + kt * (TC_KC * 4) + c * 4));
             }
-            if (it >= TC_STAGES) mbar_wait(&empty_bar[s], ((it / TC_STAGES) - 1) & 1);
-            unsigned char* st = smem + s * TC_STAGE_BYTES;
+            if (it >= NST) mbar_wait(&empty_bar[s], ((it / NST) - 1) & 1);
+            unsigned char* st = smem + s * stage_bytes;
             float4* a_hi = (float4*)st;
             float4* a_lo = (float4*)(st + TC_TILE_BYTES);
             float4* b_hi = (float4*)(st + 2 * TC_TILE_BYTES);
-            float4* b_lo = (float4*)(st + 3 * TC_TILE_BYTES);
+            float4* b_lo = (float4*)(st + 2 * TC_TILE_BYTES + a.b_tile_bytes);
             // ---- split + store
 #pragma unroll
             for (int c = 0; c < TC_KC; ++c) {
@@ -253,14 +262,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
                 float4 h, l;
                 h.x = tf32_hi(bv[j].x); h.y = tf32_hi(bv[j].y); h.z = tf32_hi(bv[j].z); h.w = tf32_hi(bv[j].w);
                 l.x = bv[j].x - h.x; l.y = bv[j].y - h.y; l.z = bv[j].z - h.z; l.w = bv[j].w - h.w;
-                b_hi[tile_idx(n, c, a.swz)] = h;
-                b_lo[tile_idx(n, c, a.swz)] = l;
+                if (n < umma_n) {                         // rows beyond the (16-padded) N tile do not exist in smem
+                    b_hi[tile_idx(n, c, a.swz)] = h;
+                    b_lo[tile_idx(n, c, a.swz)] = l;
+                }
             }
             fence_proxy_async();
             mbar_arrive(&full_bar[s]);
         }
         // ===================== epilogue =====================
-        mbar_wait(accum_bar, 0);
+        if (ktiles > 0) mbar_wait(accum_bar, 0);
         tc_fence_after();
         const int q4 = warp & 3, colhalf = warp >> 2;
         const int em = m0 + q4 * 32 + lane;
@@ -277,12 +288,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
         const long long HWout = (long long)a.Hout * a.Wout;
         for (int cg = colhalf; cg * 16 < umma_n; cg += 2) {
             float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(cg * 16), v);
-            if (a.three) {
-                float vl[16];
-                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + 128u + (uint32_t)(cg * 16), vl);
+            if (ktiles > 0) {
+                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(cg * 16), v);
+                if (a.three) {
+                    float vl[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + 128u + (uint32_t)(cg * 16), vl);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += vl[j];
+                    for (int j = 0; j < 16; ++j) v[j] += vl[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;          // empty split: contributes zeros
             }
             if (evalid) {
 #pragma unroll
@@ -291,9 +307,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
                     if (n < a.Ntot && cg * 16 + j < ntile) {
                         float o = v[j];
                         const long long off = obase + (long long)n * HWout;
-                        if (a.bias) o += __ldg(a.bias + n);
-                        if (a.res) o += __ldg(a.res + off);
-                        a.out[off] = tc_act(o, a.act, a.slope);
+                        if (a.splits > 1) {
+                            a.partial[(long long)blockIdx.z * a.out_numel + off] = o;
+                        } else {
+                            if (a.bias) o += __ldg(a.bias + n);
+                            if (a.res) o += __ldg(a.res + off);
+                            a.out[off] = tc_act(o, a.act, a.slope);
+                        }
                     }
                 }
             }
@@ -309,18 +329,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
         const uint32_t ltype = a.swz ? 2u : 0u;
         const uint32_t kstep_bytes = a.swz ? 32u : 2u * (uint32_t)(TC_M * 16);
         for (int it = 0; it < ktiles; ++it) {
-            const int s = it % TC_STAGES;
-            mbar_wait(&full_bar[s], (it / TC_STAGES) & 1);
+            const int s = it % NST;
+            mbar_wait(&full_bar[s], (it / NST) & 1);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t base = smem_u32(smem + s * TC_STAGE_BYTES);
+                const uint32_t base = smem_u32(smem + s * stage_bytes);
 #pragma unroll
                 for (int ks = 0; ks < TC_KC / 2; ++ks) {
                     const uint32_t koff = (uint32_t)ks * kstep_bytes;
                     const uint64_t ah = make_desc(base + koff, lbo, sbo, ltype);
                     const uint64_t al = make_desc(base + TC_TILE_BYTES + koff, lbo, sbo, ltype);
                     const uint64_t bh = make_desc(base + 2 * TC_TILE_BYTES + koff, lbo, sbo, ltype);
-                    const uint64_t bl = make_desc(base + 3 * TC_TILE_BYTES + koff, lbo, sbo, ltype);
+                    const uint64_t bl = make_desc(base + 2 * TC_TILE_BYTES + a.b_tile_bytes + koff, lbo, sbo, ltype);
                     // hi*hi goes to columns [0,128); the two small cross terms to [128,256): the tensor core
                     // truncates on every accumulate, so keeping the small terms out of the big accumulator
                     // (and summing them in fp32 in the epilogue) cuts the accumulated bias ~3x
@@ -369,26 +389,53 @@ __global__ void __launch_bounds__(256) wprep_kernel(const PrepArgs a) {
 
 static int roundup(int v, int m) { return (v + m - 1) / m * m; }
 
-// One generalised-fprop launch (+ its weight preparation).  Returns CCB_OK or an error.
+void launch_splitk_reduce(const float* work, float* out, const float* bias, const float* res, long long numel, int splits,
+                          int plane, int C, int act, float slope, cudaStream_t st);   // conv_ffma.cu
+
+static int tc_smem_bytes(int stages, int b_tile_bytes) { return stages * (2 * TC_TILE_BYTES + 2 * b_tile_bytes) + 2048; }
+
+// Split-K plan shared by all parity classes of one call: enough CTAs for ~2 waves, >= 2 k-tiles per split.
+static int plan_splits(long long M, int N, int max_ktiles, long long out_numel, long long part_floats) {
+    const long long tiles = (long long)cdiv((int)M, TC_M) * cdiv(N, TC_NMAX);
+    if (tiles >= 148 || max_ktiles < 4) return 1;
+    long long s = (2 * 148 + tiles - 1) / tiles;
+    if (s > max_ktiles / 2) s = max_ktiles / 2;
+    if (s > 32) s = 32;
+    if (out_numel > 0 && s * out_numel > part_floats) s = part_floats / out_numel;
+    return s < 2 ? 1 : (int)s;
+}
+
+// One generalised-fprop launch (+ its weight preparation).  `work` = [prepared weights | split-K partials].
 static int launch_tc(TcArgs& a, const float* w, int mode, int N, int Cc, int KK, int Ci, const signed char* tap_index,
-                     float* work, long long work_floats, cudaStream_t st) {
+                     float* work, long long work_floats, int splits, float* partial, cudaStream_t st) {
     a.cpad = roundup(Cc, 4);
     a.Kp = roundup(a.ntaps * a.cpad, TC_KC * 4);
     if (a.Kp == 0) a.Kp = TC_KC * 4;      // a parity class without taps still runs one all-zero k-tile
-    CCB_REQUIRE((long long)N * a.Kp <= work_floats, CCB_ERR_ARG, "conv_tc: workspace too small (%lld < %lld floats)",
-                work_floats, (long long)N * a.Kp);
+    const long long wp_floats = (long long)N * a.Kp;
+    CCB_REQUIRE(wp_floats + (splits > 1 ? (long long)splits * a.out_numel : 0) <= work_floats, CCB_ERR_ARG,
+                "conv_tc: workspace too small (%lld floats)", work_floats);
     PrepArgs p;
     p.w = w; p.wp = work; p.N = N; p.Cc = Cc; p.KK = KK; p.ntaps = a.ntaps; p.cpad = a.cpad; p.Kp = a.Kp; p.mode = mode; p.Ci = Ci;
     for (int t = 0; t < a.ntaps; ++t) p.tap_index[t] = tap_index[t];
-    long long tot = (long long)N * a.Kp;
-    CCB_LAUNCH(wprep_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, p);
+    CCB_LAUNCH(wprep_kernel, dim3((unsigned)((wp_floats + 255) / 256)), dim3(256), 0, st, p);
     int rc = check_launch("conv_tc wprep");
     if (rc) return rc;
     a.wp = work;
     a.Ntot = N;
+    a.splits = splits;
+    a.kt_per_split = cdiv(a.Kp / (TC_KC * 4), splits);
+    a.partial = partial ? partial : work + wp_floats;
+    // shared-memory geometry: the B operand only needs the (16-padded) N-tile rows; small tiles run 2 CTAs / SM
+    const int ntile_max = N < TC_NMAX ? N : TC_NMAX;
+    int nalloc = 16;
+    while (nalloc < ntile_max) nalloc <<= 1;
+    if (!a.swz) nalloc = 128;                         // the no-swizzle debug layout is [chunk][128 rows]
+    a.b_tile_bytes = nalloc * 128;
+    a.stages = (nalloc <= 64) ? 2 : TC_STAGES;
+    const int smem = tc_smem_bytes(a.stages, a.b_tile_bytes);
     { static bool once = false; if (!once) { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); once = true; } }
-    dim3 grid(cdiv(a.M, TC_M), cdiv(N, TC_NMAX));
-    CCB_LAUNCH(conv_tc_kernel, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, a);
+    dim3 grid(cdiv(a.M, TC_M), cdiv(N, TC_NMAX), splits);
+    CCB_LAUNCH(conv_tc_kernel, grid, dim3(TC_THREADS), smem, st, a);
     return check_launch("conv_tc");
 }
 
@@ -427,7 +474,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWg
     const int HWo = a.Ho * a.Wo, HWi = a.Hi * a.Wi;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS / 2); mbar_init(&empty_bar[s], 1); }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
@@ -438,26 +485,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWg
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 8) {
-        const int c = tid & 7, rbase = tid >> 3;      // chunk along K, rows rbase + 32 j
-        // decode this thread's 4 A rows (tap, ci) once
-        int a_ci[4], a_ky[4], a_kx[4];
+        // two producer groups (4 warps each) fill alternating stages; inside a group 8 consecutive threads
+        // walk the 8 K-chunks (32 consecutive pixels) of one row, rows rbase + 16 j
+        const int grp = warp >> 2;
+        const int c = tid & 7, rbase = (tid & 127) >> 3;
+        int a_ci[8], a_ky[8], a_kx[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int m = m0 + rbase + 32 * j;
+        for (int j = 0; j < 8; ++j) {
+            int m = m0 + rbase + 16 * j;
             a_ci[j] = -1; a_ky[j] = a_kx[j] = 0;
             if (m < a.Mtot) {
                 int tap = m / a.cpad, ci = m - tap * a.cpad;
                 if (ci < a.Ci) { a_ci[j] = ci; a_ky[j] = tap / a.kw; a_kx[j] = tap - a_ky[j] * a.kw; }
             }
         }
-        for (int it = 0; it < nst; ++it) {
+        for (int it = grp; it < nst; it += 2) {
             const int s = it % TC_STAGES;
-            if (it >= TC_STAGES) mbar_wait(&empty_bar[s], ((it / TC_STAGES) - 1) & 1);
-            unsigned char* st = smem + s * TC_STAGE_BYTES;
-            float4* a_hi = (float4*)st;
-            float4* a_lo = (float4*)(st + TC_TILE_BYTES);
-            float4* b_hi = (float4*)(st + 2 * TC_TILE_BYTES);
-            float4* b_lo = (float4*)(st + 3 * TC_TILE_BYTES);
             const int p0 = ((st_beg + it) * TC_KC + c) * 4;       // first of this chunk's 4 pixels
             const bool pvalid = p0 < a.P;
             int b = 0, oy = 0, ox0 = 0;
@@ -467,10 +510,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWg
                 oy = rem / a.Wo;
                 ox0 = rem - oy * a.Wo;
             }
-            float av[4][4];
-            float4 bv[4];
+            float av[8][4];
+            float4 bv[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 av[j][0] = av[j][1] = av[j][2] = av[j][3] = 0.f;
                 if (pvalid && a_ci[j] >= 0) {
                     const int iy = oy * a.stride - a.pad + a_ky[j];
@@ -485,13 +528,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWg
                     }
                 }
                 bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int n = rbase + 32 * j;
+                const int n = rbase + 16 * j;
                 if (pvalid && n < ntile)
                     bv[j] = __ldg((const float4*)(a.dy + ((long long)b * a.Co + n0 + n) * HWo + oy * a.Wo + ox0));
             }
+            if (it >= TC_STAGES) mbar_wait(&empty_bar[s], ((it / TC_STAGES) - 1) & 1);
+            unsigned char* st = smem + s * TC_STAGE_BYTES;
+            float4* a_hi = (float4*)st;
+            float4* a_lo = (float4*)(st + TC_TILE_BYTES);
+            float4* b_hi = (float4*)(st + 2 * TC_TILE_BYTES);
+            float4* b_lo = (float4*)(st + 3 * TC_TILE_BYTES);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = rbase + 32 * j;
+            for (int j = 0; j < 8; ++j) {
+                const int r = rbase + 16 * j;
                 float4 h, l;
                 h.x = tf32_hi(av[j][0]); h.y = tf32_hi(av[j][1]); h.z = tf32_hi(av[j][2]); h.w = tf32_hi(av[j][3]);
                 l.x = av[j][0] - h.x; l.y = av[j][1] - h.y; l.z = av[j][2] - h.z; l.w = av[j][3] - h.w;
@@ -613,7 +662,7 @@ static int wgrad_splits(const ccb_conv_desc* d, int& stages, int& per_split) {
     const int tiles = cdiv(d->kh * d->kw * cpad, TC_M) * cdiv(d->Co, TC_NMAX);
     int splits = cdiv(2 * 148, tiles);
     if (splits > stages / 4) splits = stages / 4;
-    if (splits > 32) splits = 32;
+    if (splits > 296) splits = 296;
     if (splits < 1) splits = 1;
     per_split = cdiv(stages, splits);
     splits = cdiv(stages, per_split);          // no empty split
@@ -628,7 +677,12 @@ long long tc_workspace_floats(const ccb_conv_desc* d, int op) {
     }
     int N = (op == CCB_CONV_FPROP) ? d->Co : d->Ci;
     int Cc = (op == CCB_CONV_FPROP) ? d->Ci : d->Co;
-    return (long long)N * roundup(d->kh * d->kw * roundup(Cc, 4), 32);
+    long long wpf = (long long)N * roundup(d->kh * d->kw * roundup(Cc, 4), 32);
+    long long out_numel = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Co * d->Ho * d->Wo : (long long)d->B * d->Ci * d->Hi * d->Wi;
+    long long M = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Ho * d->Wo : (long long)d->B * d->Hi * d->Wi / (d->stride * d->stride);
+    long long tiles = (long long)cdiv((int)M, TC_M) * cdiv(N, TC_NMAX);
+    long long part = (tiles < 148) ? 32 * out_numel : 0;       // room for up to 32 splits when the grid is small
+    return wpf + part;
 }
 
 int tc_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float* bias, const float* res, float* y,
@@ -650,17 +704,32 @@ int tc_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float
             a.off_x[t] = (signed char)(kx - d->pad);
             tix[t] = (signed char)t;
         }
-    return launch_tc(a, w, 0, d->Co, d->Ci, d->kh * d->kw, d->Ci, tix, work, work_floats, st);
+    a.out_numel = (long long)d->B * d->Co * d->Ho * d->Wo;
+    const int Kp = roundup(a.ntaps * roundup(d->Ci, 4), 32);
+    const long long wpf = (long long)d->Co * Kp;
+    const int splits = plan_splits(a.M, d->Co, Kp / 32, a.out_numel, work_floats - wpf);
+    int rc = launch_tc(a, w, 0, d->Co, d->Ci, d->kh * d->kw, d->Ci, tix, work, work_floats, splits, nullptr, st);
+    if (rc || splits == 1) return rc;
+    launch_splitk_reduce(a.partial, y, bias, res, a.out_numel, splits, d->Ho * d->Wo, d->Co, d->act, d->slope, st);
+    return check_launch("conv_tc splitk reduce");
 }
 
 // dx[b,ci,iy,ix] = sum_{co,ky,kx} dy[b,co,(iy+p-ky)/s,(ix+p-kx)/s] w[co,ci,ky,kx]   (one launch per parity class)
 int tc_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const float* bias, const float* res, float* dx,
              float* work, long long work_floats, int three, cudaStream_t st) {
     const int s = d->stride;
+    // one split-K plan for every parity class (they share the partial buffers; each writes its own pixels)
+    const long long out_numel = (long long)d->B * d->Ci * d->Hi * d->Wi;
+    const int max_taps = cdiv(d->kh, s) * cdiv(d->kw, s);
+    const int Kp_max = roundup(max_taps * roundup(d->Co, 4), 32);
+    const long long wpf_max = (long long)d->Ci * Kp_max;
+    const long long Mclass = (long long)d->B * cdiv(d->Hi, s) * cdiv(d->Wi, s);
+    const int splits = plan_splits(Mclass, d->Ci, Kp_max / 32, out_numel, work_floats - wpf_max);
     for (int py = 0; py < s && py < d->Hi; ++py)
         for (int px = 0; px < s && px < d->Wi; ++px) {
             TcArgs a;
             memset(&a, 0, sizeof(a));
+            a.out_numel = out_numel;
             a.x = dy; a.bias = bias; a.res = res; a.out = dx;
             a.B = d->B; a.Cin = d->Co; a.Hin = d->Ho; a.Win = d->Wo;
             a.Hout = d->Hi; a.Wout = d->Wi;
@@ -682,9 +751,15 @@ int tc_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const floa
                 }
             }
             a.ntaps = nt;
-            int rc = launch_tc(a, w, 1, d->Ci, d->Co, d->kh * d->kw, d->Ci, tix, work, work_floats, st);
+            // every class prepares its own weights at the start of `work`; partials live after the largest prep
+            int rc = launch_tc(a, w, 1, d->Ci, d->Co, d->kh * d->kw, d->Ci, tix, work, wpf_max + (splits > 1 ? splits * out_numel : 0),
+                               splits, work + wpf_max, st);
             if (rc) return rc;
         }
+    if (splits > 1) {
+        launch_splitk_reduce(work + wpf_max, dx, bias, res, out_numel, splits, d->Hi * d->Wi, d->Ci, d->act, d->slope, st);
+        return check_launch("conv_tc dgrad splitk reduce");
+    }
     return CCB_OK;
 }
 

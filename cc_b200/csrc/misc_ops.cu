@@ -6,50 +6,74 @@
 
 namespace ccb {
 
-// ---- BatchNorm (training): one CTA per channel ---------------------------------------------------
-// stats[c] = {mean, invstd}; running stats updated with momentum (unbiased variance), like torch.
-__global__ void __launch_bounds__(256) bn_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, float* __restrict__ y,
-                                                     float* __restrict__ stats, float* __restrict__ run_mean,
-                                                     float* __restrict__ run_var, int B, int C, int plane, float eps,
-                                                     float momentum) {
+// ---- BatchNorm (training) ---------------------------------------------------------------------------
+// Three fully parallel passes (the 1x1-downsample BNs of the decoder see 16-64 channels x 3.4 M values:
+// one CTA per channel would serialise the whole plane):
+//   1. bn_partial_kernel  : grid (C, nsplit): per-(channel, split) count / mean / M2 (two-pass inside the split)
+//   2. bn_merge_kernel    : Chan merge of the splits -> stats[c] = {mean, invstd}; running-stat update
+//   3. bn_apply_kernel    : y = (x - mean) * invstd * gamma + beta, elementwise
+constexpr int BN_CHUNK = 8192;       // elements of one (batch, channel) plane handled per split-CTA
+
+__global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict__ x, float* __restrict__ part, int B, int C,
+                                                         int plane, int nsplit) {
     __shared__ float s_red[32];
-    __shared__ float s_mean, s_inv;
-    const int c = blockIdx.x;
-    const float n = (float)B * (float)plane;
+    __shared__ float s_mean;
+    const int c = blockIdx.x, sp = blockIdx.y;
+    const long long per = (long long)B * plane;                 // values of this channel
+    const long long beg = (long long)sp * BN_CHUNK, end = min(per, beg + (long long)BN_CHUNK);
     float v[1] = {0.f};
-    for (int b = 0; b < B; ++b) {
-        const float* p = x + ((long long)b * C + c) * plane;
-        for (int i = threadIdx.x; i < plane; i += 256) v[0] += __ldg(p + i);
+    for (long long i = beg + threadIdx.x; i < end; i += 256) {
+        int b = (int)(i / plane), o = (int)(i - (long long)b * plane);
+        v[0] += __ldg(x + ((long long)b * C + c) * plane + o);
     }
     block_sum<1>(v, s_red);
+    const float n = (float)(end - beg);
     if (threadIdx.x == 0) s_mean = v[0] / n;
     __syncthreads();
     const float mean = s_mean;
     v[0] = 0.f;
-    for (int b = 0; b < B; ++b) {
-        const float* p = x + ((long long)b * C + c) * plane;
-        for (int i = threadIdx.x; i < plane; i += 256) { float d = __ldg(p + i) - mean; v[0] += d * d; }
+    for (long long i = beg + threadIdx.x; i < end; i += 256) {
+        int b = (int)(i / plane), o = (int)(i - (long long)b * plane);
+        float d = __ldg(x + ((long long)b * C + c) * plane + o) - mean;
+        v[0] += d * d;
     }
     block_sum<1>(v, s_red);
     if (threadIdx.x == 0) {
-        float var = v[0] / n;
-        s_inv = 1.f / sqrtf(var + eps);
-        stats[2 * c] = mean;
-        stats[2 * c + 1] = s_inv;
-        if (run_mean) {
-            run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
-            float unb = (n > 1.f) ? v[0] / (n - 1.f) : var;
-            run_var[c] = (1.f - momentum) * run_var[c] + momentum * unb;
-        }
+        float* p = part + ((long long)c * nsplit + sp) * 3;
+        p[0] = n; p[1] = mean; p[2] = v[0];
     }
-    __syncthreads();
-    const float inv = s_inv, g = __ldg(gamma + c), bt = __ldg(beta + c);
-    for (int b = 0; b < B; ++b) {
-        const float* p = x + ((long long)b * C + c) * plane;
-        float* q = y + ((long long)b * C + c) * plane;
-        for (int i = threadIdx.x; i < plane; i += 256) q[i] = (__ldg(p + i) - mean) * inv * g + bt;
+}
+
+__global__ void bn_merge_kernel(const float* __restrict__ part, float* __restrict__ stats, float* __restrict__ run_mean,
+                                float* __restrict__ run_var, int C, int nsplit, float eps, float momentum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float n = 0.f, mean = 0.f, m2 = 0.f;
+    for (int s = 0; s < nsplit; ++s) {                          // Chan et al. pairwise merge, fixed order
+        const float* p = part + ((long long)c * nsplit + s) * 3;
+        float nb = p[0], mb = p[1], m2b = p[2];
+        float nt = n + nb, delta = mb - mean;
+        mean += delta * (nb / nt);
+        m2 += m2b + delta * delta * (n * nb / nt);
+        n = nt;
     }
+    float var = m2 / n;
+    stats[2 * c] = mean;
+    stats[2 * c + 1] = 1.f / sqrtf(var + eps);
+    if (run_mean) {
+        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+        float unb = (n > 1.f) ? m2 / (n - 1.f) : var;
+        run_var[c] = (1.f - momentum) * run_var[c] + momentum * unb;
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float* __restrict__ stats,
+                                                       float* __restrict__ y, long long numel, int C, int plane) {
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= numel) return;
+    int c = (int)((i / plane) % C);
+    y[i] = (__ldg(x + i) - __ldg(stats + 2 * c)) * __ldg(stats + 2 * c + 1) * __ldg(gamma + c) + __ldg(beta + c);
 }
 
 // eval mode: y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta
@@ -66,43 +90,52 @@ __global__ void __launch_bounds__(256) bn_eval_kernel(const float* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                     const float* __restrict__ gamma, const float* __restrict__ stats,
-                                                     float* __restrict__ dx, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, int B, int C, int plane) {
+// backward: partial sums of (dy, dy * xhat) per (channel, split) -> reduce -> elementwise dx
+__global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                             const float* __restrict__ stats, float* __restrict__ part, int B,
+                                                             int C, int plane, int nsplit) {
     __shared__ float s_red[2 * 32];
-    __shared__ float s_a, s_b;
-    const int c = blockIdx.x;
-    const float n = (float)B * (float)plane;
-    const float mean = __ldg(stats + 2 * c), inv = __ldg(stats + 2 * c + 1), g = __ldg(gamma + c);
+    const int c = blockIdx.x, sp = blockIdx.y;
+    const long long per = (long long)B * plane;
+    const long long beg = (long long)sp * BN_CHUNK, end = min(per, beg + (long long)BN_CHUNK);
+    const float mean = __ldg(stats + 2 * c), inv = __ldg(stats + 2 * c + 1);
     float v[2] = {0.f, 0.f};
-    for (int b = 0; b < B; ++b) {
-        const float* p = x + ((long long)b * C + c) * plane;
-        const float* q = dy + ((long long)b * C + c) * plane;
-        for (int i = threadIdx.x; i < plane; i += 256) {
-            float d = __ldg(q + i);
-            v[0] += d;
-            v[1] += d * (__ldg(p + i) - mean) * inv;
-        }
+    for (long long i = beg + threadIdx.x; i < end; i += 256) {
+        int b = (int)(i / plane), o = (int)(i - (long long)b * plane);
+        long long off = ((long long)b * C + c) * plane + o;
+        float d = __ldg(dy + off);
+        v[0] += d;
+        v[1] += d * (__ldg(x + off) - mean) * inv;
     }
     block_sum<2>(v, s_red);
     if (threadIdx.x == 0) {
-        dbeta[c] = v[0];
-        dgamma[c] = v[1];
-        s_a = v[0] / n;
-        s_b = v[1] / n;
+        float* p = part + ((long long)c * nsplit + sp) * 2;
+        p[0] = v[0]; p[1] = v[1];
     }
-    __syncthreads();
-    const float ma = s_a, mb = s_b;
-    for (int b = 0; b < B; ++b) {
-        const float* p = x + ((long long)b * C + c) * plane;
-        const float* q = dy + ((long long)b * C + c) * plane;
-        float* r = dx + ((long long)b * C + c) * plane;
-        for (int i = threadIdx.x; i < plane; i += 256) {
-            float xh = (__ldg(p + i) - mean) * inv;
-            r[i] = g * inv * (__ldg(q + i) - ma - xh * mb);
-        }
-    }
+}
+
+__global__ void bn_bwd_merge_kernel(const float* __restrict__ part, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    float* __restrict__ sums, int C, int nsplit) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float a = 0.f, b = 0.f;
+    for (int s = 0; s < nsplit; ++s) { a += part[((long long)c * nsplit + s) * 2]; b += part[((long long)c * nsplit + s) * 2 + 1]; }
+    dbeta[c] = a;
+    dgamma[c] = b;
+    sums[2 * c] = a;
+    sums[2 * c + 1] = b;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                           const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                           const float* __restrict__ sums, float* __restrict__ dx,
+                                                           long long numel, int C, int plane, float inv_n) {
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= numel) return;
+    int c = (int)((i / plane) % C);
+    const float mean = __ldg(stats + 2 * c), inv = __ldg(stats + 2 * c + 1);
+    float xh = (__ldg(x + i) - mean) * inv;
+    dx[i] = __ldg(gamma + c) * inv * (__ldg(dy + i) - __ldg(sums + 2 * c) * inv_n - xh * __ldg(sums + 2 * c + 1) * inv_n);
 }
 
 // ---- bilinear x2 upsample, align_corners=False (F.interpolate scale_factor=2) ---------------------
@@ -189,14 +222,24 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 using namespace ccb;
 
+extern "C" long long ccb_bn_workspace_floats(int B, int C, int plane) {
+    long long nsplit = ((long long)B * plane + BN_CHUNK - 1) / BN_CHUNK;
+    return (long long)C * nsplit * 3 + 2 * C;
+}
+
 extern "C" int ccb_bn_fwd(const float* x, const float* gamma, const float* beta, float* y, float* stats,
                           float* running_mean, float* running_var, int B, int C, int plane, float eps, float momentum,
-                          int training, ccb_stream_t stream) {
+                          int training, float* work, ccb_stream_t stream) {
     CCB_REQUIRE(x && gamma && beta && y, CCB_ERR_ARG, "bn_fwd: null pointer");
     if (training) {
-        CCB_REQUIRE(stats != nullptr, CCB_ERR_ARG, "bn_fwd: stats null in training mode");
-        CCB_LAUNCH(bn_fwd_kernel, dim3(C), dim3(256), 0, stream, x, gamma, beta, y, stats, running_mean, running_var, B, C,
-                   plane, eps, momentum);
+        CCB_REQUIRE(stats != nullptr && work != nullptr, CCB_ERR_ARG, "bn_fwd: stats/work null in training mode");
+        const int nsplit = (int)(((long long)B * plane + BN_CHUNK - 1) / BN_CHUNK);
+        const long long numel = (long long)B * C * plane;
+        CCB_LAUNCH(bn_partial_kernel, dim3(C, nsplit), dim3(256), 0, stream, x, work, B, C, plane, nsplit);
+        CCB_LAUNCH(bn_merge_kernel, dim3(cdiv(C, 128)), dim3(128), 0, stream, (const float*)work, stats, running_mean, running_var, C,
+                   nsplit, eps, momentum);
+        CCB_LAUNCH(bn_apply_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), 0, stream, x, gamma, beta, (const float*)stats, y,
+                   numel, C, plane);
     } else {
         CCB_REQUIRE(running_mean && running_var, CCB_ERR_ARG, "bn_fwd: running stats null in eval mode");
         CCB_LAUNCH(bn_eval_kernel, dim3(C), dim3(256), 0, stream, x, gamma, beta, (const float*)running_mean,
@@ -206,9 +249,15 @@ extern "C" int ccb_bn_fwd(const float* x, const float* gamma, const float* beta,
 }
 
 extern "C" int ccb_bn_bwd(const float* x, const float* dy, const float* gamma, const float* stats, float* dx,
-                          float* dgamma, float* dbeta, int B, int C, int plane, ccb_stream_t stream) {
-    CCB_REQUIRE(x && dy && gamma && stats && dx && dgamma && dbeta, CCB_ERR_ARG, "bn_bwd: null pointer");
-    CCB_LAUNCH(bn_bwd_kernel, dim3(C), dim3(256), 0, stream, x, dy, gamma, stats, dx, dgamma, dbeta, B, C, plane);
+                          float* dgamma, float* dbeta, int B, int C, int plane, float* work, ccb_stream_t stream) {
+    CCB_REQUIRE(x && dy && gamma && stats && dx && dgamma && dbeta && work, CCB_ERR_ARG, "bn_bwd: null pointer");
+    const int nsplit = (int)(((long long)B * plane + BN_CHUNK - 1) / BN_CHUNK);
+    const long long numel = (long long)B * C * plane;
+    float* sums = work + (long long)C * nsplit * 3;
+    CCB_LAUNCH(bn_bwd_partial_kernel, dim3(C, nsplit), dim3(256), 0, stream, x, dy, stats, work, B, C, plane, nsplit);
+    CCB_LAUNCH(bn_bwd_merge_kernel, dim3(cdiv(C, 128)), dim3(128), 0, stream, (const float*)work, dgamma, dbeta, sums, C, nsplit);
+    CCB_LAUNCH(bn_bwd_apply_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), 0, stream, x, dy, gamma, stats,
+               (const float*)sums, dx, numel, C, plane, 1.f / ((float)B * (float)plane));
     return check_launch("bn_bwd");
 }
 

@@ -162,9 +162,10 @@ class _BatchNormFn(torch.autograd.Function):
         B, Cc, h, w = x.shape
         y = torch.empty_like(x)
         stats = torch.empty(Cc, 2, device=x.device) if training else None
+        work = torch.empty(_lib.lib().ccb_bn_workspace_floats(B, Cc, h * w), device=x.device) if training else None
         _lib.check(_lib.lib().ccb_bn_fwd(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(y), _lib.ptr(stats),
                                          _lib.ptr(rm), _lib.ptr(rv), B, Cc, h * w, eps, momentum, int(training),
-                                         _lib.stream(x)), 'bn_fwd')
+                                         _lib.ptr(work), _lib.stream(x)), 'bn_fwd')
         ctx.save_for_backward(x, gamma, stats)
         ctx.training = training
         return y
@@ -179,8 +180,9 @@ class _BatchNormFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         dg, g_direct = _grad_slot(ctx.params[0], gamma)
         db, b_direct = _grad_slot(ctx.params[1], gamma)
+        work = torch.empty(_lib.lib().ccb_bn_workspace_floats(B, Cc, h * w), device=x.device)
         _lib.check(_lib.lib().ccb_bn_bwd(_lib.ptr(x), _lib.ptr(g), _lib.ptr(gamma), _lib.ptr(stats), _lib.ptr(dx),
-                                         _lib.ptr(dg), _lib.ptr(db), B, Cc, h * w, _lib.stream(x)), 'bn_bwd')
+                                         _lib.ptr(dg), _lib.ptr(db), B, Cc, h * w, _lib.ptr(work), _lib.stream(x)), 'bn_bwd')
         return dx, (None if g_direct else dg), (None if b_direct else db), None, None, None, None, None
 
 

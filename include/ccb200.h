@@ -247,11 +247,12 @@ int ccb_featwarp_bwd(const float* x, const float* flow, int B, int C, int h, int
 
 /* BatchNorm2d over [B,C,plane] (DispResNet6.py:45-52).  training: batch statistics, stats[C][2] =
  * {mean, invstd} saved for backward, running stats updated in place (momentum, unbiased var). */
+long long ccb_bn_workspace_floats(int B, int C, int plane);   /* `work` size for both calls */
 int ccb_bn_fwd(const float* x, const float* gamma, const float* beta, float* y, float* stats,
                float* running_mean, float* running_var, int B, int C, int plane, float eps, float momentum,
-               int training, ccb_stream_t stream);
+               int training, float* work, ccb_stream_t stream);
 int ccb_bn_bwd(const float* x, const float* dy, const float* gamma, const float* stats, float* dx,
-               float* dgamma, float* dbeta, int B, int C, int plane, ccb_stream_t stream);
+               float* dgamma, float* dbeta, int B, int C, int plane, float* work, ccb_stream_t stream);
 /* bilinear x2 upsample, align_corners=False (DispResNet6.py:174; back2future.py:60): [planes,h,w] -> [planes,2h,2w] */
 int ccb_upsample2x_fwd(const float* x, float* y, int planes, int h, int w, ccb_stream_t stream);
 int ccb_upsample2x_bwd(const float* dy, float* dx, int planes, int h, int w, ccb_stream_t stream);

@@ -75,7 +75,8 @@ def case_conv_tc(device):
     g = torch.Generator().manual_seed(7)
     shapes = [(2, 32, 16, 24, 64, 3, 1, 1), (2, 17, 13, 20, 40, 3, 2, 1), (4, 128, 32, 104, 128, 3, 1, 1),
               (4, 32, 64, 208, 32, 7, 1, 3), (4, 65, 32, 104, 32, 1, 1, 0), (2, 256, 16, 52, 160, 3, 1, 1),
-              (2, 16, 64, 208, 1, 3, 1, 1), (4, 3, 64, 208, 32, 7, 2, 3)]
+              (2, 16, 64, 208, 1, 3, 1, 1), (4, 3, 64, 208, 32, 7, 2, 3),
+              (4, 512, 8, 26, 512, 3, 1, 1), (4, 256, 16, 52, 512, 3, 2, 1)]      # small-M layers: split-K
     saved = cnn.CONV_IMPL
     try:
         for (B, Ci, H, W, Co, k, s, p) in shapes:
@@ -99,7 +100,7 @@ def case_conv_tc(device):
                 assert_close(gw, gd[1], tol, tag + ' wgrad')
                 assert_close(gb, gd[2], tol, tag + ' bias grad')
         # ConvTranspose2d forward == strided dgrad parity classes
-        x = torch.randn(2, 96, 16, 52, generator=g).to(device).requires_grad_(True)
+        x = torch.randn(4, 96, 8, 28, generator=g).to(device).requires_grad_(True)      # small M per parity class: split-K
         b = torch.randn(32, generator=g).to(device)
         cnn.CONV_IMPL = _lib.IMPL_TC
         for (k, op) in ((4, 0), (3, 1)):
@@ -136,6 +137,16 @@ def case_bn_upsample(device):
     assert_close(bn.running_var, ref.running_var, TOL, 'bn running_var')
     bn.eval(); ref.eval()
     assert_close(bn(x), ref(x), TOL, 'bn eval')
+    # multi-split path (B*plane > 8192 values per channel) incl. a large common offset (Chan merge stability)
+    xb = (torch.randn(2, 3, 80, 70, generator=g) + 30.0).to(device).requires_grad_(True)
+    bn2, ref2 = cnn.BatchNorm2d(3).to(device), torch.nn.BatchNorm2d(3).to(device)
+    y, z = bn2(xb), ref2(xb)
+    assert_close(y, z, TOL, 'bn multi-split fwd')
+    wt = _wts(y.shape, 8, device)
+    for a_, b_, nm in zip(torch.autograd.grad((y * wt).sum(), [xb, bn2.weight, bn2.bias]),
+                          torch.autograd.grad((z * wt).sum(), [xb, ref2.weight, ref2.bias]), ('dx', 'dgamma', 'dbeta')):
+        assert_close(a_, b_, TOL, 'bn multi-split ' + nm)
+    assert_close(bn2.running_var, ref2.running_var, TOL, 'bn multi-split running_var')
     x2 = torch.randn(2, 3, 5, 9, generator=g).to(device).requires_grad_(True)
     u = cnn.upsample2x(x2)
     v = F.interpolate(x2, scale_factor=2, mode='bilinear', align_corners=False)

@@ -159,7 +159,7 @@ constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 2048;   // + barriers
 
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms are 1 KB
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms are 1 KB
     const int NST = a.stages;
     const int stage_bytes = 2 * TC_TILE_BYTES + 2 * a.b_tile_bytes;     // A hi, A lo, B hi, B lo
     uint64_t* full_bar = (uint64_t*)(smem + NST * stage_bytes);
@@ -458,7 +458,7 @@ struct TcWgradArgs {
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWgradArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full_bar = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + TC_STAGES;
     uint64_t* accum_bar = empty_bar + TC_STAGES;
@@ -652,7 +652,7 @@ bool tc_profitable(const ccb_conv_desc* d, int op) {
     int N = (op == CCB_CONV_FPROP) ? d->Co : d->Ci;
     int Cc = (op == CCB_CONV_FPROP) ? d->Ci : d->Co;
     (void)N;
-    return M >= 1024 && Cc * d->kh * d->kw >= 16;
+    return M >= 128 && Cc * d->kh * d->kw >= 16;
 }
 
 static int wgrad_splits(const ccb_conv_desc* d, int& stages, int& per_split) {

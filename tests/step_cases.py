@@ -65,4 +65,29 @@ def case_step_cfg1(device, B=2, H=128, W=416, steps=2, gtol=4e-3):
     return tr
 
 
+def case_step_cfg3(device, B=2, H=64, W=128):
+    """Full joint step (BASELINE.json configs[3] at reduced size): all five loss terms + total vs the oracle."""
+    from cc_b200.train_step import loss_cfg3, build_nets
+    tgt, refs = synth.frames(B, H, W, seed=60)
+    K, Kinv = synth.intrinsics(B, H, W)
+    P = OS.make_params('cfg3')
+    lo, auxo = OS.loss_cfg3(P, tgt, refs, K, Kinv)
+    lo.backward()
+    nets = build_nets('cfg3', device, state_dicts=_oracle_params_as_state_dicts(P))
+    dt, dr, dK, dKi = tgt.to(device), [r.to(device) for r in refs], K.to(device), Kinv.to(device)
+    lc, auxc = loss_cfg3(nets, dt, dr, dK, dKi)
+    lc.backward()
+    for k in ('loss_1', 'loss_2', 'loss_3', 'loss_4', 'loss_5'):
+        assert_close(auxc[k], auxo[k], 1e-3, 'cfg3 ' + k)
+    assert_close(lc, lo, 1e-3, 'cfg3 total loss')
+    for i in range(6):
+        assert_close(auxc['flow_fwd'][i], auxo['flow_fwd'][i], 1e-3, f'cfg3 flow_fwd{i}')
+        assert_close(auxc['emask'][i], auxo['emask'][i], 1e-3, f'cfg3 emask{i}')
+    # every parameter of every net received a gradient of the right magnitude (Back2Future's occ decoders excepted)
+    for net in ('disp', 'pose', 'mask', 'flow'):
+        go = torch.sqrt(sum((t.grad ** 2).sum() for t in P[net].values() if t.requires_grad and t.grad is not None))
+        gc = torch.sqrt(sum((p.grad ** 2).sum() for p in nets[net].parameters() if p.grad is not None))
+        assert_close(gc, go, 5e-2, f'cfg3 grad norm {net}')
+
+
 STEP_CASES_SIM = [case_flat_adam]

@@ -91,3 +91,7 @@ def test_train_step_cfg1_vs_oracle():
 
 def test_conv_tensor_core_path():
     NC.case_conv_tc(torch.device('cuda:0'))
+
+
+def test_joint_step_cfg3_vs_oracle():
+    SC.case_step_cfg3(torch.device('cuda:0'))

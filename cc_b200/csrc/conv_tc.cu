@@ -33,7 +33,7 @@ constexpr int TC_MAX_TAPS = 49;
 
 struct TcArgs {
     const float* x;        // input activations [B, Cin, Hin, Win]
-    const float* wp;       // prepared weights [N][Kp]  (k = tap * cpad + c, zero padded)
+    const float* wp;       // prepared weights: tf32 hi copy [N][Kp] followed by the lo copy [N][Kp] (k = tap*cpad + c)
     const float* bias;
     const float* res;
     float* out;            // [B, N_total, Hout, Wout]
@@ -123,6 +123,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ float tf32_hi(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -157,6 +161,7 @@ constexpr int TC_TILE_BYTES = TC_KC * TC_M * 16;                   // one operan
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                  // A hi, A lo, B hi, B lo
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 2048;   // + barriers / tmem slot / alignment slack
 
+template <bool THREE, bool SWZ>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms are 1 KB
@@ -209,35 +214,44 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcArgs a) 
         for (int it = grp; it < ktiles; it += 2) {
             const int s = it % NST;
             const int kt = kt_beg + it;                   // global k-tile
-            // ---- A: the 8 chunks (32 floats) of this thread's pixel row; tap/channel walk incrementally
+            // ---- A: the 8 chunks (32 floats) of this thread's pixel row
             float av[TC_KC][4];
-            int q = kt * TC_KC;
-            int tap = q / cpt, c4 = q - tap * cpt;
-#pragma unroll
-            for (int c = 0; c < TC_KC; ++c) {
-                av[c][0] = av[c][1] = av[c][2] = av[c][3] = 0.f;
-                if (mvalid && q < nchunks) {
-                    const int iy = iy0 + a.off_y[tap], ix = ix0 + a.off_x[tap];
-                    if (iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) {
-                        const float* p = xb + (long long)(c4 * 4) * HWin + (iy * a.Win + ix);
-                        const int nv = a.Cin - c4 * 4;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j < nv) av[c][j] = __ldg(p + j * HWin);
-                    }
+            const int q0 = kt * TC_KC;
+            const int tap0 = q0 / cpt, c40 = q0 - tap0 * cpt;
+            if (c40 + TC_KC <= cpt) {
+                // fast path (C_in % 32 == 0 layers): the whole stage reads one filter tap -> one bounds check,
+                // one base pointer, 32 loads that differ only by the channel-plane stride
+                bool ok = mvalid && tap0 < a.ntaps;
+                int pix = 0;
+                if (ok) {
+                    const int iy = iy0 + a.off_y[tap0], ix = ix0 + a.off_x[tap0];
+                    ok = (iy >= 0) && (iy < a.Hin) && (ix >= 0) && (ix < a.Win);
+                    pix = iy * a.Win + ix;
                 }
-                ++q;
-                if (++c4 == cpt) { c4 = 0; ++tap; }
-            }
-            // ---- B: 8 float4 of the prepared weight tile (pairs of threads cover one 32-byte sector)
-            float4 bv[8];
+                const float* p = xb + (long long)(c40 * 4) * HWin + pix;
+                const int nv = ok ? (a.Cin - c40 * 4) : 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int idx = r + j * 128;                      // 0 .. 1023
-                const int c = ((idx >> 8) << 1) | (idx & 1);
-                const int n = (idx >> 1) & 127;
-                bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n < ntile) bv[j] = __ldg((const float4*)(a.wp + (long long)(n0 + n) * a.Kp + kt * (TC_KC * 4) + c * 4));
+                for (int c = 0; c < TC_KC; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) av[c][j] = (c * 4 + j < nv) ? __ldg(p + (c * 4 + j) * HWin) : 0.f;
+            } else {
+                int q = q0, tap = tap0, c4 = c40;
+#pragma unroll
+                for (int c = 0; c < TC_KC; ++c) {
+                    av[c][0] = av[c][1] = av[c][2] = av[c][3] = 0.f;
+                    if (mvalid && q < nchunks) {
+                        const int iy = iy0 + a.off_y[tap], ix = ix0 + a.off_x[tap];
+                        if (iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) {
+                            const float* p = xb + (long long)(c4 * 4) * HWin + (iy * a.Win + ix);
+                            const int nv = a.Cin - c4 * 4;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (j < nv) av[c][j] = __ldg(p + j * HWin);
+                        }
+                    }
+                    ++q;
+                    if (++c4 == cpt) { c4 = 0; ++tap; }
+                }
             }
             if (it >= NST) mbar_wait(&empty_bar[s], ((it / NST) - 1) & 1);
             unsigned char* st = smem + s * stage_bytes;
@@ -245,28 +259,34 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcArgs a) 
             float4* a_lo = (float4*)(st + TC_TILE_BYTES);
             float4* b_hi = (float4*)(st + 2 * TC_TILE_BYTES);
             float4* b_lo = (float4*)(st + 2 * TC_TILE_BYTES + a.b_tile_bytes);
-            // ---- split + store
+            // ---- B: the weights were split into tf32 hi / lo by the prep kernel: plain 16-byte async copies
+            //      (pairs of threads cover one 32-byte sector of a weight row)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int idx = r + j * 128;                      // 0 .. 1023
+                const int c = ((idx >> 8) << 1) | (idx & 1);
+                const int n = (idx >> 1) & 127;
+                if (n < umma_n) {
+                    // rows in [ntile, umma_n) exist in the prepared buffer only if they are < Ntot; clamp to row 0 and
+                    // let the epilogue ignore those columns (their products never reach a stored output)
+                    const int nn = (n < ntile) ? n : 0;
+                    const float* src = a.wp + (long long)(n0 + nn) * a.Kp + kt * (TC_KC * 4) + c * 4;
+                    cp_async16(&b_hi[tile_idx(n, c, SWZ)], src);
+                    if (THREE) cp_async16(&b_lo[tile_idx(n, c, SWZ)], src + (long long)a.Ntot * a.Kp);
+                }
+            }
+            // ---- A: split + store
 #pragma unroll
             for (int c = 0; c < TC_KC; ++c) {
                 float4 h, l;
                 h.x = tf32_hi(av[c][0]); h.y = tf32_hi(av[c][1]); h.z = tf32_hi(av[c][2]); h.w = tf32_hi(av[c][3]);
-                l.x = av[c][0] - h.x; l.y = av[c][1] - h.y; l.z = av[c][2] - h.z; l.w = av[c][3] - h.w;
-                a_hi[tile_idx(r, c, a.swz)] = h;
-                a_lo[tile_idx(r, c, a.swz)] = l;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int idx = r + j * 128;
-                const int c = ((idx >> 8) << 1) | (idx & 1);
-                const int n = (idx >> 1) & 127;
-                float4 h, l;
-                h.x = tf32_hi(bv[j].x); h.y = tf32_hi(bv[j].y); h.z = tf32_hi(bv[j].z); h.w = tf32_hi(bv[j].w);
-                l.x = bv[j].x - h.x; l.y = bv[j].y - h.y; l.z = bv[j].z - h.z; l.w = bv[j].w - h.w;
-                if (n < umma_n) {                         // rows beyond the (16-padded) N tile do not exist in smem
-                    b_hi[tile_idx(n, c, a.swz)] = h;
-                    b_lo[tile_idx(n, c, a.swz)] = l;
+                a_hi[tile_idx(r, c, SWZ)] = h;
+                if (THREE) {
+                    l.x = av[c][0] - h.x; l.y = av[c][1] - h.y; l.z = av[c][2] - h.z; l.w = av[c][3] - h.w;
+                    a_lo[tile_idx(r, c, SWZ)] = l;
                 }
             }
+            cp_async_wait_all();
             fence_proxy_async();
             mbar_arrive(&full_bar[s]);
         }
@@ -290,7 +310,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcArgs a) 
             float v[16];
             if (ktiles > 0) {
                 tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(cg * 16), v);
-                if (a.three) {
+                if (THREE) {
                     float vl[16];
                     tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + 128u + (uint32_t)(cg * 16), vl);
 #pragma unroll
@@ -323,11 +343,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcArgs a) 
         // ===================== MMA issuer (one thread) =====================
         // instruction descriptor: D fp32, A/B tf32, both K-major, N = umma_n, M = 128
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-        uint32_t lbo = a.swz ? 16u : (uint32_t)(TC_M * 16);
-        uint32_t sbo = a.swz ? 1024u : 128u;
+        uint32_t lbo = SWZ ? 16u : (uint32_t)(TC_M * 16);
+        uint32_t sbo = SWZ ? 1024u : 128u;
         if (a.swap_lbo_sbo) { uint32_t t = lbo; lbo = sbo; sbo = t; }
-        const uint32_t ltype = a.swz ? 2u : 0u;
-        const uint32_t kstep_bytes = a.swz ? 32u : 2u * (uint32_t)(TC_M * 16);
+        const uint32_t ltype = SWZ ? 2u : 0u;
+        const uint32_t kstep_bytes = SWZ ? 32u : 2u * (uint32_t)(TC_M * 16);
         for (int it = 0; it < ktiles; ++it) {
             const int s = it % NST;
             mbar_wait(&full_bar[s], (it / NST) & 1);
@@ -345,7 +365,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcArgs a) 
                     // truncates on every accumulate, so keeping the small terms out of the big accumulator
                     // (and summing them in fp32 in the epilogue) cuts the accumulated bias ~3x
                     umma_tf32(tmem_base, ah, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-                    if (a.three) {
+                    if (THREE) {
                         umma_tf32(tmem_base + 128u, al, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
                         umma_tf32(tmem_base + 128u, ah, bl, idesc, 1u);
                     }
@@ -384,7 +404,9 @@ __global__ void __launch_bounds__(256) wprep_kernel(const PrepArgs a) {
         v = (a.mode == 0) ? __ldg(a.w + ((long long)n * a.Cc + c) * a.KK + tap)
                           : __ldg(a.w + ((long long)c * a.Ci + n) * a.KK + tap);
     }
-    a.wp[i] = v;
+    const float h = tf32_hi(v);
+    a.wp[i] = h;                                        // hi copy [N][Kp]
+    a.wp[(long long)a.N * a.Kp + i] = v - h;            // lo copy right behind it
 }
 
 static int roundup(int v, int m) { return (v + m - 1) / m * m; }
@@ -411,13 +433,13 @@ static int launch_tc(TcArgs& a, const float* w, int mode, int N, int Cc, int KK,
     a.cpad = roundup(Cc, 4);
     a.Kp = roundup(a.ntaps * a.cpad, TC_KC * 4);
     if (a.Kp == 0) a.Kp = TC_KC * 4;      // a parity class without taps still runs one all-zero k-tile
-    const long long wp_floats = (long long)N * a.Kp;
+    const long long wp_floats = 2ll * N * a.Kp;                  // tf32 hi copy + lo copy
     CCB_REQUIRE(wp_floats + (splits > 1 ? (long long)splits * a.out_numel : 0) <= work_floats, CCB_ERR_ARG,
                 "conv_tc: workspace too small (%lld floats)", work_floats);
     PrepArgs p;
     p.w = w; p.wp = work; p.N = N; p.Cc = Cc; p.KK = KK; p.ntaps = a.ntaps; p.cpad = a.cpad; p.Kp = a.Kp; p.mode = mode; p.Ci = Ci;
     for (int t = 0; t < a.ntaps; ++t) p.tap_index[t] = tap_index[t];
-    CCB_LAUNCH(wprep_kernel, dim3((unsigned)((wp_floats + 255) / 256)), dim3(256), 0, st, p);
+    CCB_LAUNCH(wprep_kernel, dim3((unsigned)(((long long)N * a.Kp + 255) / 256)), dim3(256), 0, st, p);
     int rc = check_launch("conv_tc wprep");
     if (rc) return rc;
     a.wp = work;
@@ -433,9 +455,11 @@ static int launch_tc(TcArgs& a, const float* w, int mode, int N, int Cc, int KK,
     a.b_tile_bytes = nalloc * 128;
     a.stages = (nalloc <= 64) ? 2 : TC_STAGES;
     const int smem = tc_smem_bytes(a.stages, a.b_tile_bytes);
-    { static bool once = false; if (!once) { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); once = true; } }
     dim3 grid(cdiv(a.M, TC_M), cdiv(N, TC_NMAX), splits);
-    CCB_LAUNCH(conv_tc_kernel, grid, dim3(TC_THREADS), smem, st, a);
+    auto kfn = a.swz ? (a.three ? conv_tc_kernel<true, true> : conv_tc_kernel<false, true>)
+                     : (a.three ? conv_tc_kernel<true, false> : conv_tc_kernel<false, false>);
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    CCB_LAUNCH(kfn, grid, dim3(TC_THREADS), smem, st, a);
     return check_launch("conv_tc");
 }
 
@@ -456,6 +480,7 @@ struct TcWgradArgs {
     int three, swz, swap_lbo_sbo;
 };
 
+template <bool THREE, bool SWZ>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWgradArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -544,12 +569,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWg
                 float4 h, l;
                 h.x = tf32_hi(av[j][0]); h.y = tf32_hi(av[j][1]); h.z = tf32_hi(av[j][2]); h.w = tf32_hi(av[j][3]);
                 l.x = av[j][0] - h.x; l.y = av[j][1] - h.y; l.z = av[j][2] - h.z; l.w = av[j][3] - h.w;
-                a_hi[tile_idx(r, c, a.swz)] = h;
-                a_lo[tile_idx(r, c, a.swz)] = l;
+                a_hi[tile_idx(r, c, SWZ)] = h;
+                a_lo[tile_idx(r, c, SWZ)] = l;
                 h.x = tf32_hi(bv[j].x); h.y = tf32_hi(bv[j].y); h.z = tf32_hi(bv[j].z); h.w = tf32_hi(bv[j].w);
                 l.x = bv[j].x - h.x; l.y = bv[j].y - h.y; l.z = bv[j].z - h.z; l.w = bv[j].w - h.w;
-                b_hi[tile_idx(r, c, a.swz)] = h;
-                b_lo[tile_idx(r, c, a.swz)] = l;
+                b_hi[tile_idx(r, c, SWZ)] = h;
+                b_lo[tile_idx(r, c, SWZ)] = l;
             }
             fence_proxy_async();
             mbar_arrive(&full_bar[s]);
@@ -569,7 +594,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWg
         for (int cg = colhalf; cg * 16 < umma_n; cg += 2) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(cg * 16), v);
-            if (a.three) {
+            if (THREE) {
                 float vl[16];
                 tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + 128u + (uint32_t)(cg * 16), vl);
 #pragma unroll
@@ -586,11 +611,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWg
         tc_fence_before();
     } else {
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-        uint32_t lbo = a.swz ? 16u : (uint32_t)(TC_M * 16);
-        uint32_t sbo = a.swz ? 1024u : 128u;
+        uint32_t lbo = SWZ ? 16u : (uint32_t)(TC_M * 16);
+        uint32_t sbo = SWZ ? 1024u : 128u;
         if (a.swap_lbo_sbo) { uint32_t t = lbo; lbo = sbo; sbo = t; }
-        const uint32_t ltype = a.swz ? 2u : 0u;
-        const uint32_t kstep_bytes = a.swz ? 32u : 2u * (uint32_t)(TC_M * 16);
+        const uint32_t ltype = SWZ ? 2u : 0u;
+        const uint32_t kstep_bytes = SWZ ? 32u : 2u * (uint32_t)(TC_M * 16);
         for (int it = 0; it < nst; ++it) {
             const int s = it % TC_STAGES;
             mbar_wait(&full_bar[s], (it / TC_STAGES) & 1);
@@ -608,7 +633,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWg
                     // truncates on every accumulate, so keeping the small terms out of the big accumulator
                     // (and summing them in fp32 in the epilogue) cuts the accumulated bias ~3x
                     umma_tf32(tmem_base, ah, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-                    if (a.three) {
+                    if (THREE) {
                         umma_tf32(tmem_base + 128u, al, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
                         umma_tf32(tmem_base + 128u, ah, bl, idesc, 1u);
                     }
@@ -651,8 +676,8 @@ bool tc_profitable(const ccb_conv_desc* d, int op) {
     long long M = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Ho * d->Wo : (long long)d->B * d->Hi * d->Wi;
     int N = (op == CCB_CONV_FPROP) ? d->Co : d->Ci;
     int Cc = (op == CCB_CONV_FPROP) ? d->Ci : d->Co;
-    (void)N;
-    return M >= 128 && Cc * d->kh * d->kw >= 16;
+    (void)N; (void)Cc;
+    return M >= 128 && (long long)d->Ci * d->Co * d->kh * d->kw >= 64;
 }
 
 static int wgrad_splits(const ccb_conv_desc* d, int& stages, int& per_split) {
@@ -677,7 +702,7 @@ long long tc_workspace_floats(const ccb_conv_desc* d, int op) {
     }
     int N = (op == CCB_CONV_FPROP) ? d->Co : d->Ci;
     int Cc = (op == CCB_CONV_FPROP) ? d->Ci : d->Co;
-    long long wpf = (long long)N * roundup(d->kh * d->kw * roundup(Cc, 4), 32);
+    long long wpf = 2ll * N * roundup(d->kh * d->kw * roundup(Cc, 4), 32);
     long long out_numel = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Co * d->Ho * d->Wo : (long long)d->B * d->Ci * d->Hi * d->Wi;
     long long M = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Ho * d->Wo : (long long)d->B * d->Hi * d->Wi / (d->stride * d->stride);
     long long tiles = (long long)cdiv((int)M, TC_M) * cdiv(N, TC_NMAX);
@@ -706,7 +731,7 @@ int tc_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float
         }
     a.out_numel = (long long)d->B * d->Co * d->Ho * d->Wo;
     const int Kp = roundup(a.ntaps * roundup(d->Ci, 4), 32);
-    const long long wpf = (long long)d->Co * Kp;
+    const long long wpf = 2ll * d->Co * Kp;
     const int splits = plan_splits(a.M, d->Co, Kp / 32, a.out_numel, work_floats - wpf);
     int rc = launch_tc(a, w, 0, d->Co, d->Ci, d->kh * d->kw, d->Ci, tix, work, work_floats, splits, nullptr, st);
     if (rc || splits == 1) return rc;
@@ -722,7 +747,7 @@ int tc_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const floa
     const long long out_numel = (long long)d->B * d->Ci * d->Hi * d->Wi;
     const int max_taps = cdiv(d->kh, s) * cdiv(d->kw, s);
     const int Kp_max = roundup(max_taps * roundup(d->Co, 4), 32);
-    const long long wpf_max = (long long)d->Ci * Kp_max;
+    const long long wpf_max = 2ll * d->Ci * Kp_max;
     const long long Mclass = (long long)d->B * cdiv(d->Hi, s) * cdiv(d->Wi, s);
     const int splits = plan_splits(Mclass, d->Ci, Kp_max / 32, out_numel, work_floats - wpf_max);
     for (int py = 0; py < s && py < d->Hi; ++py)
@@ -782,9 +807,11 @@ int tc_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw,
     } else {
         a.out = dw;
     }
-    { static bool once = false; if (!once) { cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); once = true; } }
     dim3 grid(cdiv(a.Mtot, TC_M), cdiv(d->Co, TC_NMAX), a.splits);
-    CCB_LAUNCH(conv_tc_wgrad_kernel, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, a);
+    auto kfn = a.swz ? (a.three ? conv_tc_wgrad_kernel<true, true> : conv_tc_wgrad_kernel<false, true>)
+                     : (a.three ? conv_tc_wgrad_kernel<true, false> : conv_tc_wgrad_kernel<false, false>);
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    CCB_LAUNCH(kfn, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, a);
     int rc = check_launch("conv_tc_wgrad");
     if (rc || a.splits == 1) return rc;
     CCB_LAUNCH(tc_splitk_sum_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), 0, st, (const float*)work, dw, numel, a.splits);

@@ -478,13 +478,16 @@ struct TcWgradArgs {
     int P;               // B*Ho*Wo pixels (Wo % 4 == 0)
     int stages, per_split, splits;
     int three, swz, swap_lbo_sbo;
+    int nstages, b_tile_bytes;   // pipeline depth / bytes of one dY operand copy (Co-tile dependent)
 };
 
 template <bool THREE, bool SWZ>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWgradArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_wgrad_kernel(const TcWgradArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* full_bar = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
+    const int NST = a.nstages;
+    const int stage_bytes = 2 * TC_TILE_BYTES + 2 * a.b_tile_bytes;
+    uint64_t* full_bar = (uint64_t*)(smem + NST * stage_bytes);
     uint64_t* empty_bar = full_bar + TC_STAGES;
     uint64_t* accum_bar = empty_bar + TC_STAGES;
     uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWg
     const int HWo = a.Ho * a.Wo, HWi = a.Hi * a.Wi;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS / 2); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS / 2); mbar_init(&empty_bar[s], 1); }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
@@ -514,18 +517,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWg
         // walk the 8 K-chunks (32 consecutive pixels) of one row, rows rbase + 16 j
         const int grp = warp >> 2;
         const int c = tid & 7, rbase = (tid & 127) >> 3;
-        int a_ci[8], a_ky[8], a_kx[8];
+        // per-row constants: x offset of the row's (ci, ky, kx) relative to the pixel base, and its tap shift
+        int rowoff[8], dky[8], dkx[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             int m = m0 + rbase + 16 * j;
-            a_ci[j] = -1; a_ky[j] = a_kx[j] = 0;
+            rowoff[j] = -1; dky[j] = dkx[j] = 0;
             if (m < a.Mtot) {
                 int tap = m / a.cpad, ci = m - tap * a.cpad;
-                if (ci < a.Ci) { a_ci[j] = ci; a_ky[j] = tap / a.kw; a_kx[j] = tap - a_ky[j] * a.kw; }
+                if (ci < a.Ci) {
+                    int ky = tap / a.kw, kx = tap - ky * a.kw;
+                    dky[j] = ky - a.pad; dkx[j] = kx - a.pad;
+                    rowoff[j] = ci * HWi + dky[j] * a.Wi + dkx[j];       // >= -(pad*Wi+pad): flagged by dky/dkx checks below
+                    if (rowoff[j] < 0) rowoff[j] += 0;                  // (kept as is; validity is tracked by `rvalid`)
+                }
             }
         }
+        unsigned rvalid = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int m = m0 + rbase + 16 * j;
+            if (m < a.Mtot && (m - (m / a.cpad) * a.cpad) < a.Ci) rvalid |= 1u << j;
+        }
         for (int it = grp; it < nst; it += 2) {
-            const int s = it % TC_STAGES;
+            const int s = it % NST;
             const int p0 = ((st_beg + it) * TC_KC + c) * 4;       // first of this chunk's 4 pixels
             const bool pvalid = p0 < a.P;
             int b = 0, oy = 0, ox0 = 0;
@@ -535,20 +550,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWg
                 oy = rem / a.Wo;
                 ox0 = rem - oy * a.Wo;
             }
+            const float* xpix = a.x + (long long)b * a.Ci * HWi + (oy * a.stride) * a.Wi + ox0 * a.stride;
+            const int iyb = oy * a.stride, ixb = ox0 * a.stride;
             float av[8][4];
             float4 bv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 av[j][0] = av[j][1] = av[j][2] = av[j][3] = 0.f;
-                if (pvalid && a_ci[j] >= 0) {
-                    const int iy = oy * a.stride - a.pad + a_ky[j];
-                    if (iy >= 0 && iy < a.Hi) {
-                        const float* px = a.x + ((long long)b * a.Ci + a_ci[j]) * HWi + iy * a.Wi;
-                        const int ix0 = ox0 * a.stride - a.pad + a_kx[j];
+                const int iy = iyb + dky[j], ix0 = ixb + dkx[j];
+                if (pvalid && ((rvalid >> j) & 1u) && iy >= 0 && iy < a.Hi) {
+                    const float* px = xpix + rowoff[j];
+                    if (ix0 >= 0 && ix0 + 3 * a.stride < a.Wi) {          // interior: no per-element checks
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) av[j][e] = __ldg(px + e * a.stride);
+                    } else {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int ix = ix0 + e * a.stride;
-                            if (ix >= 0 && ix < a.Wi) av[j][e] = __ldg(px + ix);
+                            if (ix >= 0 && ix < a.Wi) av[j][e] = __ldg(px + e * a.stride);
                         }
                     }
                 }
@@ -557,24 +576,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWg
                 if (pvalid && n < ntile)
                     bv[j] = __ldg((const float4*)(a.dy + ((long long)b * a.Co + n0 + n) * HWo + oy * a.Wo + ox0));
             }
-            if (it >= TC_STAGES) mbar_wait(&empty_bar[s], ((it / TC_STAGES) - 1) & 1);
-            unsigned char* st = smem + s * TC_STAGE_BYTES;
+            if (it >= NST) mbar_wait(&empty_bar[s], ((it / NST) - 1) & 1);
+            unsigned char* st = smem + s * stage_bytes;
             float4* a_hi = (float4*)st;
             float4* a_lo = (float4*)(st + TC_TILE_BYTES);
             float4* b_hi = (float4*)(st + 2 * TC_TILE_BYTES);
-            float4* b_lo = (float4*)(st + 3 * TC_TILE_BYTES);
+            float4* b_lo = (float4*)(st + 2 * TC_TILE_BYTES + a.b_tile_bytes);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int r = rbase + 16 * j;
                 float4 h, l;
                 h.x = tf32_hi(av[j][0]); h.y = tf32_hi(av[j][1]); h.z = tf32_hi(av[j][2]); h.w = tf32_hi(av[j][3]);
-                l.x = av[j][0] - h.x; l.y = av[j][1] - h.y; l.z = av[j][2] - h.z; l.w = av[j][3] - h.w;
                 a_hi[tile_idx(r, c, SWZ)] = h;
-                a_lo[tile_idx(r, c, SWZ)] = l;
-                h.x = tf32_hi(bv[j].x); h.y = tf32_hi(bv[j].y); h.z = tf32_hi(bv[j].z); h.w = tf32_hi(bv[j].w);
-                l.x = bv[j].x - h.x; l.y = bv[j].y - h.y; l.z = bv[j].z - h.z; l.w = bv[j].w - h.w;
-                b_hi[tile_idx(r, c, SWZ)] = h;
-                b_lo[tile_idx(r, c, SWZ)] = l;
+                if (THREE) {
+                    l.x = av[j][0] - h.x; l.y = av[j][1] - h.y; l.z = av[j][2] - h.z; l.w = av[j][3] - h.w;
+                    a_lo[tile_idx(r, c, SWZ)] = l;
+                }
+                if (r < umma_n) {
+                    h.x = tf32_hi(bv[j].x); h.y = tf32_hi(bv[j].y); h.z = tf32_hi(bv[j].z); h.w = tf32_hi(bv[j].w);
+                    b_hi[tile_idx(r, c, SWZ)] = h;
+                    if (THREE) {
+                        l.x = bv[j].x - h.x; l.y = bv[j].y - h.y; l.z = bv[j].z - h.z; l.w = bv[j].w - h.w;
+                        b_lo[tile_idx(r, c, SWZ)] = l;
+                    }
+                }
             }
             fence_proxy_async();
             mbar_arrive(&full_bar[s]);
@@ -617,21 +642,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_wgrad_kernel(const TcWg
         const uint32_t ltype = SWZ ? 2u : 0u;
         const uint32_t kstep_bytes = SWZ ? 32u : 2u * (uint32_t)(TC_M * 16);
         for (int it = 0; it < nst; ++it) {
-            const int s = it % TC_STAGES;
-            mbar_wait(&full_bar[s], (it / TC_STAGES) & 1);
+            const int s = it % NST;
+            mbar_wait(&full_bar[s], (it / NST) & 1);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t base = smem_u32(smem + s * TC_STAGE_BYTES);
+                const uint32_t base = smem_u32(smem + s * stage_bytes);
 #pragma unroll
                 for (int ks = 0; ks < TC_KC / 2; ++ks) {
                     const uint32_t koff = (uint32_t)ks * kstep_bytes;
                     const uint64_t ah = make_desc(base + koff, lbo, sbo, ltype);
                     const uint64_t al = make_desc(base + TC_TILE_BYTES + koff, lbo, sbo, ltype);
                     const uint64_t bh = make_desc(base + 2 * TC_TILE_BYTES + koff, lbo, sbo, ltype);
-                    const uint64_t bl = make_desc(base + 3 * TC_TILE_BYTES + koff, lbo, sbo, ltype);
-                    // hi*hi goes to columns [0,128); the two small cross terms to [128,256): the tensor core
-                    // truncates on every accumulate, so keeping the small terms out of the big accumulator
-                    // (and summing them in fp32 in the epilogue) cuts the accumulated bias ~3x
+                    const uint64_t bl = make_desc(base + 2 * TC_TILE_BYTES + a.b_tile_bytes + koff, lbo, sbo, ltype);
                     umma_tf32(tmem_base, ah, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
                     if (THREE) {
                         umma_tf32(tmem_base + 128u, al, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
@@ -807,11 +829,20 @@ int tc_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw,
     } else {
         a.out = dw;
     }
+    {
+        const int ntile_max = d->Co < TC_NMAX ? d->Co : TC_NMAX;
+        int nalloc = 16;
+        while (nalloc < ntile_max) nalloc <<= 1;
+        if (!a.swz) nalloc = 128;
+        a.b_tile_bytes = nalloc * 128;
+        a.nstages = (nalloc <= 64) ? 2 : TC_STAGES;
+    }
+    const int wsmem = tc_smem_bytes(a.nstages, a.b_tile_bytes);
     dim3 grid(cdiv(a.Mtot, TC_M), cdiv(d->Co, TC_NMAX), a.splits);
     auto kfn = a.swz ? (a.three ? conv_tc_wgrad_kernel<true, true> : conv_tc_wgrad_kernel<false, true>)
                      : (a.three ? conv_tc_wgrad_kernel<true, false> : conv_tc_wgrad_kernel<false, false>);
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    CCB_LAUNCH(kfn, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, a);
+    CCB_LAUNCH(kfn, grid, dim3(TC_THREADS), wsmem, st, a);
     int rc = check_launch("conv_tc_wgrad");
     if (rc || a.splits == 1) return rc;
     CCB_LAUNCH(tc_splitk_sum_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), 0, st, (const float*)work, dw, numel, a.splits);

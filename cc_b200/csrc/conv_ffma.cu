@@ -385,6 +385,21 @@ int tc_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const floa
 int tc_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw, float* work, long long work_floats,
              int three, cudaStream_t st);
 
+// TMA-fed tensor-core path (conv_tma.cu): stride-1 gathers (FPROP stride 1, every DGRAD parity class)
+bool tma_conv_supported(const ccb_conv_desc* d, int op);
+long long tma_workspace_floats(const ccb_conv_desc* d, int op);
+int tma_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float* bias, const float* res, float* y,
+              float* work, long long work_floats, int three, cudaStream_t st);
+int tma_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const float* bias, const float* res, float* dx,
+              float* work, long long work_floats, int three, cudaStream_t st);
+bool tma_wgrad_supported(const ccb_conv_desc* d);
+long long tma_wgrad_workspace_floats(const ccb_conv_desc* d);
+int tma_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw, float* work, long long work_floats, int three,
+              cudaStream_t st);
+static bool use_tma(const ccb_conv_desc* d, int op, const void* src) {
+    return (((uintptr_t)src) & 15) == 0 && tma_conv_supported(d, op) && tma_workspace_floats(d, op) >= 0;
+}
+
 // 0: FFMA, 1: tcgen05 3xTF32, 2: tcgen05 single TF32
 static int pick_impl(const ccb_conv_desc* d, int op) {
     switch (d->impl) {
@@ -405,6 +420,14 @@ extern "C" long long ccb_conv_workspace_floats(const ccb_conv_desc* d, int op) {
     const long long bias_need = (op == CCB_CONV_WGRAD) ? (long long)d->Co * (((long long)d->B * d->Ho * d->Wo + BG_CHUNK - 1) / BG_CHUNK) : 0;
     if (d->impl != CCB_CONV_IMPL_FFMA && tc_supported(d, op) && pick_impl(d, op) > 0) {
         long long t = tc_workspace_floats(d, op);
+        if (op != CCB_CONV_WGRAD && tma_conv_supported(d, op)) {
+            long long t2 = tma_workspace_floats(d, op);
+            if (t2 > t) t = t2;
+        }
+        if (op == CCB_CONV_WGRAD && tma_wgrad_supported(d)) {
+            long long t2 = tma_wgrad_workspace_floats(d);
+            if (t2 > t) t = t2;
+        }
         return t > bias_need ? t : bias_need;
     }
     long long numel = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Co * d->Ho * d->Wo
@@ -427,6 +450,8 @@ extern "C" int ccb_conv2d_fprop(const ccb_conv_desc* d, const float* x, const fl
     {
         int impl = pick_impl(d, CCB_CONV_FPROP);
         CCB_REQUIRE(impl >= 0, CCB_ERR_UNSUPPORTED, "conv2d_fprop: shape not supported by the tensor-core path");
+        if (impl > 0 && use_tma(d, CCB_CONV_FPROP, x))
+            return tma_fprop(d, x, w, bias, res, y, work, work_floats, impl == 1, (cudaStream_t)stream);
         if (impl > 0) return tc_fprop(d, x, w, bias, res, y, work, work_floats, impl == 1, (cudaStream_t)stream);
     }
     a.x = x; a.w = w; a.bias = bias; a.res = res; a.out = y; a.work = work;
@@ -444,6 +469,8 @@ extern "C" int ccb_conv2d_dgrad(const ccb_conv_desc* d, const float* dy, const f
     {
         int impl = pick_impl(d, CCB_CONV_DGRAD);
         CCB_REQUIRE(impl >= 0, CCB_ERR_UNSUPPORTED, "conv2d_dgrad: shape not supported by the tensor-core path");
+        if (impl > 0 && use_tma(d, CCB_CONV_DGRAD, dy))
+            return tma_dgrad(d, dy, w, bias, res, dx, work, work_floats, impl == 1, (cudaStream_t)stream);
         if (impl > 0) return tc_dgrad(d, dy, w, bias, res, dx, work, work_floats, impl == 1, (cudaStream_t)stream);
     }
     a.dy = dy; a.w = w; a.bias = bias; a.res = res; a.out = dx; a.work = work;
@@ -478,7 +505,10 @@ extern "C" int ccb_conv2d_wgrad(const ccb_conv_desc* d, const float* x, const fl
         int impl = pick_impl(d, CCB_CONV_WGRAD);
         CCB_REQUIRE(impl >= 0, CCB_ERR_UNSUPPORTED, "conv2d_wgrad: shape not supported by the tensor-core path");
         if (impl > 0) {
-            rc = tc_wgrad(d, x, dy, dw, work, work_floats, impl == 1, (cudaStream_t)stream);
+            if (tma_wgrad_supported(d) && ((((uintptr_t)x) | ((uintptr_t)dy)) & 15) == 0)
+                rc = tma_wgrad(d, x, dy, dw, work, work_floats, impl == 1, (cudaStream_t)stream);
+            else
+                rc = tc_wgrad(d, x, dy, dw, work, work_floats, impl == 1, (cudaStream_t)stream);
             if (rc) return rc;
             if (db) rc = launch_bias_grad(dy, db, d->B, d->Co, d->Ho * d->Wo, work, work_floats, (cudaStream_t)stream);
             return rc;

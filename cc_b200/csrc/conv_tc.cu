@@ -849,7 +849,8 @@ int tc_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw,
     return check_launch("conv_tc_wgrad_reduce");
 }
 
-void tc_set_debug_swap(int v) { g_tc_swap = v & 1; g_tc_swz = (v & 4) ? 0 : 1; }
+void tma_set_enabled(int v);   // conv_tma.cu
+void tc_set_debug_swap(int v) { g_tc_swap = v & 1; g_tc_swz = (v & 4) ? 0 : 1; tma_set_enabled(((v & 8) ? 0 : 1) | ((v & 16) ? 2 : 0)); }
 
 }  // namespace ccb
 

@@ -1,0 +1,1316 @@
+// conv_tma.cu - TMA-fed tcgen05 implicit-GEMM convolution (stride-1 gathers: every stride-1 FPROP, every
+// DGRAD parity class, ConvTranspose2d forward).
+//
+//   one CTA = 128 output pixels (4 image rows x 32 columns) x N <= 128 channels
+//   per k-stage (K = 32):
+//     A  (activations, MN-major): 4 x (32/cb) TMA boxes  (32 px, 1 row, cb channels) straight from the NCHW
+//        tensor at the tap-shifted coordinate - the box IS the im2col tile: zero padding, image borders and
+//        channel tails are the TMA's out-of-bounds zero fill, SWIZZLE_128B puts it in the UMMA layout;
+//     B  (weights, K-major):     1 (+1) TMA box (32 k, N rows) from the tf32-split weight buffer;
+//     3xTF32: eight warps compute lo = x - trunc_tf32(x) smem -> smem (elementwise, layout agnostic); the MMA
+//        reads the raw fp32 tile as the hi operand (kind::tf32 ignores the 13 low mantissa bits);
+//     one elected thread issues hi*hi (+ lo*hi + hi*lo into a second TMEM accumulator) and commits.
+//   No register staging of operands, no per-element index math, producers = ONE thread: the pipeline depth is
+//   bounded by shared memory only (3 stages of 64 KB in 3xTF32, 6 stages of 32 KB in single-TF32 mode).
+#include "ccb_common.cuh"
+
+#ifndef CCB_CPU_SIM
+#include <cstdlib>
+#include <cuda.h>   // CUtensorMap + enums only; cuTensorMapEncodeTiled is fetched through the runtime (no libcuda link)
+
+namespace ccb {
+
+constexpr int TM_M = 128;
+constexpr int TM_THREADS = 320;            // warp 0: TMA, warp 1: MMA + TMEM, warps 2..9: lo-pass + epilogue
+constexpr int TM_MAX_SLOTS = 64;           // tap slots (taps padded to a multiple of 32/cb)
+constexpr int TM_A_BYTES = 16384;          // one A operand copy of one stage: 128 px x 32 k x 4 B
+
+struct TmaConvArgs {
+    int B, Cin, Hin, Win;
+    int Ntot, Hout, Wout, Hc, Wc;
+    int out_stride, out_oy, out_ox;
+    int ntaps, cb, cblocks, units, ktiles;   // cb: channels per unit (8/16/32); units = ntaps * cblocks
+    int tiles_x, tiles_y;
+    int splits, kt_per_split;
+    long long out_numel;
+    float* partial;
+    const float* bias;
+    const float* res;
+    float* out;
+    int act;
+    float slope;
+    int nstages, b_tile_bytes, nalloc, soft, dbg;
+    signed char off_y[TM_MAX_SLOTS], off_x[TM_MAX_SLOTS];
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tm_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void tm_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tm_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool tm_mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// A wait that cannot complete is a protocol bug: fail the launch instead of hanging the box.  With the bring-up
+// switch (ccb_debug_tc_swap_strides bit 4) the first timeout is recorded in g_tma_status and every wait of the
+// launch falls through, so that the probe can report WHO waited on WHAT without losing the CUDA context.
+__device__ unsigned int g_tma_status[4];
+__device__ __noinline__ void tm_wait_failed(int soft, int role, int it) {
+    if (!soft) asm volatile("trap;");
+    if (atomicCAS(&g_tma_status[0], 0u, (unsigned)role) == 0u) {
+        g_tma_status[1] = (unsigned)it;
+        g_tma_status[2] = blockIdx.x;
+        g_tma_status[3] = blockIdx.z;
+    }
+}
+__device__ __forceinline__ void tm_mbar_wait(uint64_t* bar, uint32_t parity, int soft, int role, int it) {
+    uint32_t spins = 0;
+    while (!tm_mbar_try(bar, parity)) {
+        ++spins;
+        if (soft && (spins & 1023u) == 0 && *(volatile unsigned int*)&g_tma_status[0] != 0u) return;
+        if (spins > (soft ? (1u << 20) : (1u << 26))) { tm_wait_failed(soft, role, it); return; }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(smem_addr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_addr(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_addr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_addr(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tm_umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tm_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tm_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// shared-memory matrix descriptor (version 1); layout 2 = SWIZZLE_128B (16 B chunks), 1 = SWIZZLE_128B_BASE32B (32 B
+// chunks, 4-row atoms: the only layout the tensor core accepts for an MN-major tf32 operand)
+__device__ __forceinline__ uint64_t tm_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+__device__ __forceinline__ float tm_act(float v, int act, float slope) {
+    switch (act) {
+        case CCB_ACT_RELU: return fmaxf(v, 0.f);
+        case CCB_ACT_LEAKY: return v > 0.f ? v : v * slope;
+        case CCB_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        default: return v;
+    }
+}
+
+template <bool THREE>
+__global__ void __launch_bounds__(TM_THREADS, 1)
+conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TmaConvArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    const int NST = a.nstages;
+    const int stage_bytes = (THREE ? 2 : 1) * (TM_A_BYTES + a.b_tile_bytes);   // [A raw | A lo] [B hi | B lo]
+    uint64_t* tma_full = (uint64_t*)(smem + NST * stage_bytes);
+    uint64_t* split_full = tma_full + 8;
+    uint64_t* empty_bar = split_full + 8;
+    uint64_t* accum_bar = empty_bar + 8;
+    uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // tile -> (batch, 4-row band, 32-column block)
+    int t = blockIdx.x;
+    const int per_b = a.tiles_x * a.tiles_y;
+    const int b = t / per_b;
+    t -= b * per_b;
+    const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+    const int x0 = tx * 32, y0 = ty * 4;
+    const int n0 = blockIdx.y * 128;
+    const int ntile = min(128, a.Ntot - n0);
+    const int umma_n = (ntile + 15) & ~15;
+    const int kt_beg = blockIdx.z * a.kt_per_split;
+    const int ktiles = max(0, min(a.ktiles, kt_beg + a.kt_per_split) - kt_beg);
+    const int ups = 32 / a.cb;                       // units (tap, channel-block) per stage
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) {
+            tm_mbar_init(&tma_full[s], 1);
+            tm_mbar_init(&split_full[s], 256);
+            tm_mbar_init(&empty_bar[s], 1);
+        }
+        tm_mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t tx_bytes = (uint32_t)(TM_A_BYTES + (THREE ? 2 : 1) * a.b_tile_bytes);
+            for (int it = 0; it < ktiles; ++it) {
+                const int s = it % NST;
+                if (it >= NST) tm_mbar_wait(&empty_bar[s], ((it / NST) - 1) & 1, a.soft, 1, it);
+                unsigned char* st = smem + s * stage_bytes;
+                unsigned char* a_raw = st;
+                unsigned char* b_hi = st + (THREE ? 2 : 1) * TM_A_BYTES;
+                tm_mbar_expect_tx(&tma_full[s], tx_bytes);
+                const int kt = kt_beg + it;
+                for (int u = 0; u < ups; ++u) {
+                    int unit = kt * ups + u;
+                    int slot = 0, c0 = 0;
+                    if (unit < a.units) { slot = unit / a.cblocks; c0 = (unit - slot * a.cblocks) * a.cb; }
+                    // (units beyond the real K range multiply zero weights: any in-range coordinate will do)
+                    int X = x0 + a.off_x[slot];
+                    if (a.dbg & 8) X = x0 + 4 * a.off_x[slot];
+                    if ((a.dbg & 1) && X < 0) X = 0;
+#pragma unroll
+                    for (int mb = 0; mb < 4; ++mb) {
+                        int Y = y0 + mb + a.off_y[slot];
+                        if ((a.dbg & 2) && Y < 0) Y = 0;
+                        if ((a.dbg & 4) && Y >= a.Hin) Y = a.Hin - 1;
+                        tma_load_4d(a_raw + mb * 4096 + u * (a.cb * 128), &map_a, &tma_full[s], X, Y, c0, b);
+                    }
+                }
+                tma_load_2d(b_hi, &map_b, &tma_full[s], kt * 32, n0);
+                if (THREE) tma_load_2d(b_hi + a.b_tile_bytes, &map_b, &tma_full[s], kt * 32, a.Ntot + n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        // D fp32, A/B tf32, A MN-major (pixels contiguous), B K-major, N = umma_n, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(umma_n >> 3) << 17) |
+                               ((uint32_t)(TM_M >> 4) << 24);
+        for (int it = 0; it < ktiles; ++it) {
+            const int s = it % NST;
+            tm_mbar_wait(&tma_full[s], (it / NST) & 1, a.soft, 2, it);
+            if (THREE) tm_mbar_wait(&split_full[s], (it / NST) & 1, a.soft, 3, it);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t st = smem_addr(smem + s * stage_bytes);
+                const uint32_t a_raw = st, a_lo = st + TM_A_BYTES;
+                const uint32_t b_hi = st + (THREE ? 2 : 1) * TM_A_BYTES, b_lo = b_hi + a.b_tile_bytes;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    // A (MN-major): 32-pixel blocks 4096 B apart (LBO), 4-channel swizzle atoms 512 B apart (SBO)
+                    const uint64_t ah = tm_desc(a_raw + ks * 1024, 4096, 512, 1);
+                    // B (K-major): 8-row groups 1024 B apart (SBO); a k-step advances 32 B inside the 128 B row
+                    const uint64_t bh = tm_desc(b_hi + ks * 32, 16, 1024, 2);
+                    tm_umma_tf32(tmem_base, ah, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                    if (THREE) {
+                        const uint64_t al = tm_desc(a_lo + ks * 1024, 4096, 512, 1);
+                        const uint64_t bl = tm_desc(b_lo + ks * 32, 16, 1024, 2);
+                        tm_umma_tf32(tmem_base + 128u, al, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                        tm_umma_tf32(tmem_base + 128u, ah, bl, idesc, 1u);
+                    }
+                }
+                tm_commit(&empty_bar[s]);
+                if (it == ktiles - 1) tm_commit(accum_bar);
+            }
+            __syncwarp();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ===================== lo-pass (3xTF32) + epilogue: 8 warps =====================
+        const int wt = tid - 64;                       // 0 .. 255
+        if (THREE) {
+            for (int it = 0; it < ktiles; ++it) {
+                const int s = it % NST;
+                tm_mbar_wait(&tma_full[s], (it / NST) & 1, a.soft, 4, it);
+                float4* raw = (float4*)(smem + s * stage_bytes);
+                float4* lo = raw + TM_A_BYTES / 16;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = wt + j * 256;            // 1024 float4 per stage
+                    float4 v = raw[i], l;
+                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    lo[i] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tm_mbar_arrive(&split_full[s]);
+            }
+        }
+        if (ktiles > 0) tm_mbar_wait(accum_bar, 0, a.soft, 5, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q4 = warp & 3, colhalf = (warp - 2) >> 2;
+        const int oy = y0 + q4, ox = x0 + lane;        // TMEM lane m = 32 * row-in-tile + column-in-tile
+        const bool evalid = (oy < a.Hc) && (ox < a.Wc);
+        const long long HWout = (long long)a.Hout * a.Wout;
+        const long long obase = (long long)b * a.Ntot * HWout + (long long)(oy * a.out_stride + a.out_oy) * a.Wout +
+                                (ox * a.out_stride + a.out_ox);
+        for (int cg = colhalf; cg * 16 < umma_n; cg += 2) {
+            float v[16];
+            if (ktiles > 0) {
+                tm_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(cg * 16), v);
+                if (THREE) {
+                    float vl[16];
+                    tm_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + 128u + (uint32_t)(cg * 16), vl);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += vl[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+            if (evalid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + cg * 16 + j;
+                    if (cg * 16 + j < ntile) {
+                        float o = v[j];
+                        const long long off = obase + (long long)n * HWout;
+                        if (a.splits > 1) {
+                            a.partial[(long long)blockIdx.z * a.out_numel + off] = o;
+                        } else {
+                            if (a.bias) o += __ldg(a.bias + n);
+                            if (a.res) o += __ldg(a.res + off);
+                            a.out[off] = tm_act(o, a.act, a.slope);
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+// weight preparation for the TMA path: wp[n][u*cb + j] = w[...][tap(slot(u))], split into tf32 hi / lo copies
+struct TmaPrepArgs {
+    const float* w;
+    float* wp;
+    int N, Cc, KK, Ci, mode, cb, cblocks, units, Kp;
+    signed char tap_index[TM_MAX_SLOTS];
+};
+__global__ void __launch_bounds__(256) tma_wprep_kernel(const TmaPrepArgs a) {
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)a.N * a.Kp) return;
+    const int n = (int)(i / a.Kp), k = (int)(i - (long long)n * a.Kp);
+    const int unit = k / a.cb, j = k - unit * a.cb;
+    float v = 0.f;
+    if (unit < a.units) {
+        const int slot = unit / a.cblocks, c = (unit - slot * a.cblocks) * a.cb + j;
+        const int tap = a.tap_index[slot];
+        if (c < a.Cc && tap >= 0)
+            v = (a.mode == 0) ? __ldg(a.w + ((long long)n * a.Cc + c) * a.KK + tap) : __ldg(a.w + ((long long)c * a.Ci + n) * a.KK + tap);
+    }
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    const float h = __uint_as_float(hb);
+    a.wp[i] = h;
+    a.wp[(long long)a.N * a.Kp + i] = v - h;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+void launch_splitk_reduce(const float* work, float* out, const float* bias, const float* res, long long numel, int splits,
+                          int plane, int C, int act, float slope, cudaStream_t st);   // conv_ffma.cu
+
+static int g_tma_enabled = 1, g_tma_soft = 0;
+void tma_set_enabled(int v) { g_tma_enabled = v & 1; g_tma_soft = (v >> 1) & 1; }
+
+// Which problems the TMA path takes: stride-1 gathers on tensors whose row pitch is 16-byte aligned.
+// One launch: gathered tensor x [B, Cc, Hin, Win] -> output grid (Hc x Wc) written with stride / offset.
+static int launch_tma(const float* x, int B, int Cc, int Hin, int Win, const float* w, int mode, int N, int KK, int Ci,
+                      const int* off_y, const int* off_x, const int* tap_index, int ntaps, int Hc, int Wc, int Hout, int Wout,
+                      int out_stride, int out_oy, int out_ox, const float* bias, const float* res, float* out, int act,
+                      float slope, int three, float* work, long long work_floats, int splits, float* partial,
+                      long long out_numel, cudaStream_t st) {
+    EncodeTiledFn enc = get_encode();
+    CCB_REQUIRE(enc != nullptr, CCB_ERR_UNSUPPORTED, "conv_tma: cuTensorMapEncodeTiled unavailable");
+    TmaConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.Cin = Cc; a.Hin = Hin; a.Win = Win; a.Ntot = N; a.Hout = Hout; a.Wout = Wout; a.Hc = Hc; a.Wc = Wc;
+    a.out_stride = out_stride; a.out_oy = out_oy; a.out_ox = out_ox;
+    a.cb = Cc >= 32 ? 32 : (Cc > 8 ? 16 : 8);
+    a.cblocks = cdiv(Cc, a.cb);
+    a.ntaps = ntaps;
+    a.units = ntaps * a.cblocks;
+    const int Kp = cdiv(a.units * a.cb, 32) * 32 > 0 ? cdiv(a.units * a.cb, 32) * 32 : 32;
+    a.ktiles = Kp / 32;
+    a.tiles_x = cdiv(Wc, 32); a.tiles_y = cdiv(Hc, 4);
+    a.splits = splits; a.kt_per_split = cdiv(a.ktiles, splits);
+    a.out_numel = out_numel; a.partial = partial;
+    a.bias = bias; a.res = res; a.out = out; a.act = act; a.slope = slope; a.soft = g_tma_soft;
+    { const char* e = getenv("CCB_TMA_DBG"); a.dbg = e ? atoi(e) : 0; }
+    TmaPrepArgs p;
+    memset(&p, 0, sizeof(p));
+    CCB_REQUIRE(ntaps <= TM_MAX_SLOTS, CCB_ERR_ARG, "conv_tma: too many taps");
+    for (int t = 0; t < TM_MAX_SLOTS; ++t) {
+        a.off_y[t] = (signed char)(t < ntaps ? off_y[t] : 0);
+        a.off_x[t] = (signed char)(t < ntaps ? off_x[t] : 0);
+        p.tap_index[t] = (signed char)(t < ntaps ? tap_index[t] : -1);
+    }
+    const long long wp_floats = 2ll * N * Kp;
+    CCB_REQUIRE(wp_floats <= work_floats, CCB_ERR_ARG, "conv_tma: workspace too small");
+    p.w = w; p.wp = work; p.N = N; p.Cc = Cc; p.KK = KK; p.Ci = Ci; p.mode = mode; p.cb = a.cb; p.cblocks = a.cblocks;
+    p.units = a.units; p.Kp = Kp;
+    CCB_LAUNCH(tma_wprep_kernel, dim3((unsigned)(((long long)N * Kp + 255) / 256)), dim3(256), 0, st, p);
+    int rc = check_launch("conv_tma wprep");
+    if (rc) return rc;
+    const int ntile_max = N < 128 ? N : 128;
+    int nalloc = 16;
+    while (nalloc < ntile_max) nalloc <<= 1;
+    a.nalloc = nalloc;
+    a.b_tile_bytes = nalloc * 128;
+    const int stage_bytes = (three ? 2 : 1) * (TM_A_BYTES + a.b_tile_bytes);
+    a.nstages = (200 * 1024) / stage_bytes;
+    if (a.nstages > 8) a.nstages = 8;
+    if (a.nstages < 2) a.nstages = 2;
+    const int smem = a.nstages * stage_bytes + 2048;
+    // tensor maps.  A: x as (W, H, C, B), box (32, 1, cb, 1), SWIZZLE_128B_ATOM_32B, OOB -> 0.  B: wp as (Kp, 2N), box (32, nalloc).
+    alignas(64) CUtensorMap map_a, map_b;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)Cc, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)Win * 4, (cuuint64_t)Win * Hin * 4, (cuuint64_t)Win * Hin * Cc * 4};
+        cuuint32_t box[4] = {32, 1, (cuuint32_t)a.cb, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CCB_REQUIRE(r == CUDA_SUCCESS, CCB_ERR_LAUNCH, "conv_tma: cuTensorMapEncodeTiled(A) failed (%d)", (int)r);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)(2 * N)};
+        cuuint64_t strides[1] = {(cuuint64_t)Kp * 4};
+        cuuint32_t box[2] = {32, (cuuint32_t)nalloc};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)work, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CCB_REQUIRE(r == CUDA_SUCCESS, CCB_ERR_LAUNCH, "conv_tma: cuTensorMapEncodeTiled(B) failed (%d)", (int)r);
+    }
+    dim3 grid(B * a.tiles_x * a.tiles_y, cdiv(N, 128), splits);
+    auto kfn = three ? conv_tma_kernel<true> : conv_tma_kernel<false>;
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    CCB_LAUNCH(kfn, grid, dim3(TM_THREADS), smem, st, map_a, map_b, a);
+    return check_launch("conv_tma");
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Slab kernel: FPROP (stride 1 and 2) and every DGRAD parity class with arbitrary tap offsets.
+//   TMA can only start a box on a 16-byte boundary of the innermost (W) dimension, so a tap shifted by one pixel
+//   cannot be fetched as a box of its own.  Instead ONE aligned box per channel block - the input patch under the
+//   whole 4 x 32 output tile, every tap included, zero padding = OOB fill - lands in shared memory once (the
+//   "slab", [channel][row][column], no swizzle), and eight warps cut the per-tap operand tiles out of it:
+//   element (pixel, k = (tap, channel)) -> MN-major SWIZZLE_128B_BASE32B tile, written twice: the fp32 value (the
+//   tensor core reads its tf32 truncation) and the truncation remainder (3xTF32).
+//   K is the flattened (tap, channel) index of the block, padded to 32 once per block: no per-tap padding.
+//   MMA per 8-deep k step:  D[:, 0:2n)  += A_hi * [B_hi | B_lo]   (hi*hi and hi*lo share one read of A_hi)
+//                           D[:, 256:+n) += A_lo * B_hi
+// ---------------------------------------------------------------------------------------------------------------
+struct SlabArgs {
+    int B, Cin, Hin, Win;
+    int Ntot, Hout, Wout, Hc, Wc;
+    int out_stride, out_oy, out_ox, in_stride;
+    int ntaps;
+    int cs, cblocks, kt_full, ktiles;       // channels per slab, slabs, k-stages of a full slab, k-stages in total
+    int SW, SH, ox_lo, oy_lo, slab_bytes, slab_tx, nslab;
+    int tiles_x, tiles_y, splits, kt_per_split;
+    long long out_numel;
+    float* partial;
+    const float* bias;
+    const float* res;
+    float* out;
+    int act;
+    float slope;
+    int nstages, nbox, b_tile_bytes, soft;
+    signed char off_y[TM_MAX_SLOTS], off_x[TM_MAX_SLOTS];
+};
+
+template <bool THREE>
+__global__ void __launch_bounds__(TM_THREADS, 1)
+conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b, const SlabArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    const int NST = a.nstages;
+    const int stage_bytes = (THREE ? 2 : 1) * TM_A_BYTES + a.b_tile_bytes;     // [A hi | A lo] [B hi ; B lo]
+    unsigned char* slab0 = smem + NST * stage_bytes;
+    uint64_t* bars = (uint64_t*)(slab0 + a.nslab * a.slab_bytes);
+    uint64_t* a_full = bars;             // [8]  256 cutter threads
+    uint64_t* b_full = bars + 8;         // [8]  TMA weights
+    uint64_t* empty_bar = bars + 16;     // [8]  tcgen05.commit
+    uint64_t* slab_full = bars + 24;     // [2]  TMA slab
+    uint64_t* slab_empty = bars + 26;    // [2]  256 cutter threads
+    uint64_t* accum_bar = bars + 28;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 29);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int t = blockIdx.x;
+    const int per_b = a.tiles_x * a.tiles_y;
+    const int b = t / per_b;
+    t -= b * per_b;
+    const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+    const int x0 = tx * 32, y0 = ty * 4;
+    const int n0 = blockIdx.y * 128;
+    const int ntile = min(128, a.Ntot - n0);
+    const int kt_beg = blockIdx.z * a.kt_per_split;
+    const int ktiles = max(0, min(a.ktiles, kt_beg + a.kt_per_split) - kt_beg);
+    const int s_in = a.in_stride;
+    const int xs = (x0 * s_in + a.ox_lo) & ~3;                    // aligned slab origin (may be negative: OOB fill)
+    const int dx0 = x0 * s_in + a.ox_lo - xs;
+    const int ys = y0 * s_in + a.oy_lo;
+    const int first_block = min(kt_beg / a.kt_full, a.cblocks - 1);
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) {
+            tm_mbar_init(&a_full[s], 256);
+            tm_mbar_init(&b_full[s], 1);
+            tm_mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            tm_mbar_init(&slab_full[s], 1);
+            tm_mbar_init(&slab_empty[s], 256);
+        }
+        tm_mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one thread): slabs + weight tiles =====================
+        if (lane == 0) {
+            int issued = 0;                                        // slabs requested so far
+            const int last_block = (ktiles > 0) ? min((kt_beg + ktiles - 1) / a.kt_full, a.cblocks - 1) : first_block - 1;
+            for (int it = 0; it < ktiles; ++it) {
+                const int kt = kt_beg + it;
+                const int cblock = min(kt / a.kt_full, a.cblocks - 1);
+                // the slab of this block, and (double buffered) the next one as soon as this block starts
+                const int want = min(last_block, cblock + (a.nslab - 1)) - first_block + 1;
+                while (issued < want) {
+                    const int sb = issued % a.nslab;
+                    if (issued >= a.nslab) tm_mbar_wait(&slab_empty[sb], ((issued / a.nslab) - 1) & 1, a.soft, 6, it);
+                    tm_mbar_expect_tx(&slab_full[sb], (uint32_t)a.slab_tx);
+                    tma_load_4d(slab0 + sb * a.slab_bytes, &map_x, &slab_full[sb], xs, ys, (first_block + issued) * a.cs, b);
+                    ++issued;
+                }
+                const int s = it % NST;
+                if (it >= NST) tm_mbar_wait(&empty_bar[s], ((it / NST) - 1) & 1, a.soft, 1, it);
+                unsigned char* bt = smem + s * stage_bytes + (THREE ? 2 : 1) * TM_A_BYTES;
+                tm_mbar_expect_tx(&b_full[s], (uint32_t)((THREE ? 2 : 1) * a.nbox * 128));
+                tma_load_2d(bt, &map_b, &b_full[s], kt * 32, n0);
+                if (THREE) tma_load_2d(bt + a.nbox * 128, &map_b, &b_full[s], kt * 32, a.Ntot + n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(TM_M >> 4) << 24);
+        const uint32_t idesc_n1 = idesc_base | ((uint32_t)(a.nbox >> 3) << 17);
+        const uint32_t idesc_n2 = idesc_base | ((uint32_t)((2 * a.nbox) >> 3) << 17);
+        for (int it = 0; it < ktiles; ++it) {
+            const int s = it % NST;
+            tm_mbar_wait(&b_full[s], (it / NST) & 1, a.soft, 2, it);
+            tm_mbar_wait(&a_full[s], (it / NST) & 1, a.soft, 3, it);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t st = smem_addr(smem + s * stage_bytes);
+                const uint32_t a_hi = st, a_lo = st + TM_A_BYTES;
+                const uint32_t bt = st + (THREE ? 2 : 1) * TM_A_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t ah = tm_desc(a_hi + ks * 1024, 4096, 512, 1);
+                    const uint64_t bh = tm_desc(bt + ks * 32, 16, 1024, 2);
+                    const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+                    tm_umma_tf32(tmem_base, ah, bh, THREE ? idesc_n2 : idesc_n1, acc);
+                    if (THREE) {
+                        const uint64_t al = tm_desc(a_lo + ks * 1024, 4096, 512, 1);
+                        tm_umma_tf32(tmem_base + 256u, al, bh, idesc_n1, acc);
+                    }
+                }
+                tm_commit(&empty_bar[s]);
+                if (it == ktiles - 1) tm_commit(accum_bar);
+            }
+            __syncwarp();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ===================== cutters (8 warps): slab -> operand tiles; then the epilogue =====================
+        const int w8 = warp - 2;                               // this warp owns k rows 4*w8 .. 4*w8+3 of every stage
+        const int plane = a.SH * a.SW;
+        for (int it = 0; it < ktiles; ++it) {
+            const int kt = kt_beg + it;
+            const int cblock = min(kt / a.kt_full, a.cblocks - 1);
+            const int q = cblock - first_block;
+            const float* slab = (const float*)(slab0 + (q % a.nslab) * a.slab_bytes);
+            const bool first_of_block = (it == 0) || (min((kt - 1) / a.kt_full, a.cblocks - 1) != cblock);
+            const bool last_of_block = (it == ktiles - 1) || (min((kt + 1) / a.kt_full, a.cblocks - 1) != cblock);
+            if (first_of_block) tm_mbar_wait(&slab_full[q % a.nslab], (q / a.nslab) & 1, a.soft, 4, it);
+            const int s = it % NST;
+            if (it >= NST) tm_mbar_wait(&empty_bar[s], ((it / NST) - 1) & 1, a.soft, 7, it);
+            unsigned char* st = smem + s * stage_bytes;
+            const int nch = min(a.cs, a.Cin - cblock * a.cs);
+            int kl = (kt - cblock * a.kt_full) * 32 + w8 * 4;      // flattened (tap, channel) index inside the block
+            int tap = kl / nch, c = kl - tap * nch;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = w8 * 4 + i;
+                const bool kvalid = tap < a.ntaps;
+                const int src = kvalid ? c * plane + (a.off_y[tap] - a.oy_lo) * a.SW + (a.off_x[tap] - a.ox_lo) + dx0 + lane * s_in : 0;
+                const uint32_t dst = (uint32_t)(k * 128 + ((((lane >> 3) ^ (k & 3))) << 5) + (lane & 7) * 4);
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb) {
+                    const float v = kvalid ? slab[src + mb * s_in * a.SW] : 0.f;
+                    *(float*)(st + mb * 4096 + dst) = v;
+                    if (THREE) *(float*)(st + TM_A_BYTES + mb * 4096 + dst) = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                }
+                if (++c == nch) { c = 0; ++tap; }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tm_mbar_arrive(&a_full[s]);
+            if (last_of_block) tm_mbar_arrive(&slab_empty[q % a.nslab]);
+        }
+        if (ktiles > 0) tm_mbar_wait(accum_bar, 0, a.soft, 5, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q4 = warp & 3, colhalf = (warp - 2) >> 2;
+        const int oy = y0 + q4, ox = x0 + lane;
+        const bool evalid = (oy < a.Hc) && (ox < a.Wc);
+        const long long HWout = (long long)a.Hout * a.Wout;
+        const long long obase = (long long)b * a.Ntot * HWout + (long long)(oy * a.out_stride + a.out_oy) * a.Wout +
+                                (ox * a.out_stride + a.out_ox);
+        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        for (int cg = colhalf; cg * 16 < ntile; cg += 2) {
+            float v[16];
+            if (ktiles > 0) {
+                tm_ld16(trow + (uint32_t)(cg * 16), v);
+                if (THREE) {
+                    float v2[16];
+                    tm_ld16(trow + (uint32_t)(a.nbox + cg * 16), v2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                    tm_ld16(trow + 256u + (uint32_t)(cg * 16), v2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+            if (evalid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + cg * 16 + j;
+                    if (cg * 16 + j < ntile) {
+                        float o = v[j];
+                        const long long off = obase + (long long)n * HWout;
+                        if (a.splits > 1) {
+                            a.partial[(long long)blockIdx.z * a.out_numel + off] = o;
+                        } else {
+                            if (a.bias) o += __ldg(a.bias + n);
+                            if (a.res) o += __ldg(a.res + off);
+                            a.out[off] = tm_act(o, a.act, a.slope);
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// weights for the slab kernel: wp[n][kt*32 + j], k-stage kt -> (block, flattened (tap, channel) index), tf32 hi / lo copies
+struct SlabPrepArgs {
+    const float* w;
+    float* wp;
+    int N, Cc, KK, Ci, mode, cs, cblocks, kt_full, Kp, ntaps;
+    signed char tap_index[TM_MAX_SLOTS];
+};
+__global__ void __launch_bounds__(256) slab_wprep_kernel(const SlabPrepArgs a) {
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)a.N * a.Kp) return;
+    const int n = (int)(i / a.Kp), k = (int)(i - (long long)n * a.Kp);
+    const int kt = k >> 5;
+    const int cblock = min(kt / a.kt_full, a.cblocks - 1);
+    const int kl = (kt - cblock * a.kt_full) * 32 + (k & 31);
+    const int nch = min(a.cs, a.Cc - cblock * a.cs);
+    const int slot = kl / nch, c = cblock * a.cs + (kl - slot * nch);
+    float v = 0.f;
+    if (slot < a.ntaps) {
+        const int tap = a.tap_index[slot];
+        v = (a.mode == 0) ? __ldg(a.w + ((long long)n * a.Cc + c) * a.KK + tap) : __ldg(a.w + ((long long)c * a.Ci + n) * a.KK + tap);
+    }
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    const float h = __uint_as_float(hb);
+    a.wp[i] = h;
+    a.wp[(long long)a.N * a.Kp + i] = v - h;
+}
+
+struct SlabPlan {
+    int cs, cblocks, kt_full, ktiles, SW, SH, ox_lo, oy_lo, slab_bytes, nslab, nstages, nbox, b_tile_bytes, smem;
+    bool ok;
+};
+// tap offsets (in gathered-tensor pixels), gather stride, channels, output channels -> tiling of the K dimension
+static SlabPlan slab_plan(const int* off_y, const int* off_x, int ntaps, int in_stride, int Cc, int N, int three) {
+    SlabPlan p;
+    memset(&p, 0, sizeof(p));
+    int oxl = 0, oxh = 0, oyl = 0, oyh = 0;
+    for (int t = 0; t < ntaps; ++t) {
+        if (t == 0 || off_x[t] < oxl) oxl = off_x[t];
+        if (t == 0 || off_x[t] > oxh) oxh = off_x[t];
+        if (t == 0 || off_y[t] < oyl) oyl = off_y[t];
+        if (t == 0 || off_y[t] > oyh) oyh = off_y[t];
+    }
+    p.ox_lo = oxl; p.oy_lo = oyl;
+    p.SW = (31 * in_stride + (oxh - oxl) + 1 + 3 + 3) & ~3;
+    p.SH = 3 * in_stride + (oyh - oyl) + 1;
+    const int ntile = N < 128 ? N : 128;
+    p.nbox = (ntile + 15) & ~15;
+    p.b_tile_bytes = (three ? 2 : 1) * p.nbox * 128;
+    const int stage = (three ? 2 : 1) * TM_A_BYTES + p.b_tile_bytes;
+    const int per_ch = p.SH * p.SW * 4;
+    const int nt = ntaps > 0 ? ntaps : 1;
+    int g = nt, r = 32;                    // channel granularity that makes cs * ntaps a multiple of 32
+    while (r) { int q = g % r; g = r; r = q; }
+    const int align = 32 / g;
+    const int total = 225 * 1024;
+    for (int nst = 3; nst >= 2 && !p.ok; --nst) {
+        const int budget = total - nst * stage;
+        for (int cb = 1; cb <= Cc && !p.ok; ++cb) {
+            int cs = cdiv(Cc, cb);
+            if (cb > 1) cs = cdiv(cs, align) * align;
+            if (cs > 256 || cs < 1) continue;
+            const int cblocks = cdiv(Cc, cs);
+            const int nslab = cblocks > 1 ? 2 : 1;
+            const int sbytes = cdiv(cs * per_ch, 128) * 128;
+            if (nslab * sbytes > budget) continue;
+            p.cs = cs; p.cblocks = cblocks; p.nslab = nslab; p.slab_bytes = sbytes;
+            p.nstages = (total - nslab * sbytes) / stage;
+            if (p.nstages > 6) p.nstages = 6;
+            p.ok = true;
+        }
+    }
+    if (!p.ok) return p;
+    p.kt_full = cdiv(p.cs * nt, 32);
+    const int tail = Cc - (p.cblocks - 1) * p.cs;
+    p.ktiles = (p.cblocks - 1) * p.kt_full + cdiv(tail * nt, 32);
+    p.smem = p.nstages * stage + p.nslab * p.slab_bytes + 512 + 1024;
+    return p;
+}
+
+static int launch_slab(const float* x, int B, int Cc, int Hin, int Win, const float* w, int mode, int N, int KK, int Ci,
+                       const int* off_y, const int* off_x, const int* tap_index, int ntaps, int in_stride, int Hc, int Wc, int Hout,
+                       int Wout, int out_stride, int out_oy, int out_ox, const float* bias, const float* res, float* out, int act,
+                       float slope, int three, float* work, long long wp_floats, int splits, float* partial, long long out_numel,
+                       cudaStream_t st) {
+    EncodeTiledFn enc = get_encode();
+    CCB_REQUIRE(enc != nullptr, CCB_ERR_UNSUPPORTED, "conv_slab: cuTensorMapEncodeTiled unavailable");
+    CCB_REQUIRE(ntaps <= TM_MAX_SLOTS, CCB_ERR_ARG, "conv_slab: too many taps");
+    const SlabPlan p = slab_plan(off_y, off_x, ntaps, in_stride, Cc, N, three);
+    CCB_REQUIRE(p.ok, CCB_ERR_UNSUPPORTED, "conv_slab: no tiling fits shared memory");
+    SlabArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.Cin = Cc; a.Hin = Hin; a.Win = Win; a.Ntot = N; a.Hout = Hout; a.Wout = Wout; a.Hc = Hc; a.Wc = Wc;
+    a.out_stride = out_stride; a.out_oy = out_oy; a.out_ox = out_ox; a.in_stride = in_stride;
+    a.ntaps = ntaps; a.cs = p.cs; a.cblocks = p.cblocks; a.kt_full = p.kt_full; a.ktiles = p.ktiles;
+    a.SW = p.SW; a.SH = p.SH; a.ox_lo = p.ox_lo; a.oy_lo = p.oy_lo; a.slab_bytes = p.slab_bytes; a.slab_tx = p.cs * p.SH * p.SW * 4; a.nslab = p.nslab;
+    a.tiles_x = cdiv(Wc, 32); a.tiles_y = cdiv(Hc, 4);
+    a.splits = splits; a.kt_per_split = cdiv(a.ktiles, splits);
+    a.out_numel = out_numel; a.partial = partial;
+    a.bias = bias; a.res = res; a.out = out; a.act = act; a.slope = slope; a.soft = g_tma_soft;
+    a.nstages = p.nstages; a.nbox = p.nbox; a.b_tile_bytes = p.b_tile_bytes;
+    SlabPrepArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    for (int t = 0; t < TM_MAX_SLOTS; ++t) {
+        a.off_y[t] = (signed char)(t < ntaps ? off_y[t] : 0);
+        a.off_x[t] = (signed char)(t < ntaps ? off_x[t] : 0);
+        pa.tap_index[t] = (signed char)(t < ntaps ? tap_index[t] : 0);
+    }
+    const int Kp = a.ktiles * 32;
+    CCB_REQUIRE(2ll * N * Kp <= wp_floats, CCB_ERR_ARG, "conv_slab: workspace too small");
+    pa.w = w; pa.wp = work; pa.N = N; pa.Cc = Cc; pa.KK = KK; pa.Ci = Ci; pa.mode = mode; pa.cs = p.cs; pa.cblocks = p.cblocks;
+    pa.kt_full = p.kt_full; pa.Kp = Kp; pa.ntaps = ntaps;
+    CCB_LAUNCH(slab_wprep_kernel, dim3((unsigned)(((long long)N * Kp + 255) / 256)), dim3(256), 0, st, pa);
+    int rc = check_launch("conv_slab wprep");
+    if (rc) return rc;
+    alignas(64) CUtensorMap map_x, map_b;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)Cc, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)Win * 4, (cuuint64_t)Win * Hin * 4, (cuuint64_t)Win * Hin * Cc * 4};
+        cuuint32_t box[4] = {(cuuint32_t)p.SW, (cuuint32_t)p.SH, (cuuint32_t)p.cs, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CCB_REQUIRE(r == CUDA_SUCCESS, CCB_ERR_LAUNCH, "conv_slab: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)(2 * N)};
+        cuuint64_t strides[1] = {(cuuint64_t)Kp * 4};
+        cuuint32_t box[2] = {32, (cuuint32_t)p.nbox};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)work, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CCB_REQUIRE(r == CUDA_SUCCESS, CCB_ERR_LAUNCH, "conv_slab: cuTensorMapEncodeTiled(w) failed (%d)", (int)r);
+    }
+    dim3 grid(B * a.tiles_x * a.tiles_y, cdiv(N, 128), splits);
+    auto kfn = three ? conv_slab_kernel<true> : conv_slab_kernel<false>;
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    CCB_LAUNCH(kfn, grid, dim3(TM_THREADS), p.smem, st, map_x, map_b, a);
+    return check_launch("conv_slab");
+}
+
+// tap lists: offsets are in pixels of the gathered tensor, tap_index addresses the kh*kw weight plane
+static int fprop_taps(const ccb_conv_desc* d, int* oy, int* ox, int* tix) {
+    for (int ky = 0; ky < d->kh; ++ky)
+        for (int kx = 0; kx < d->kw; ++kx) {
+            const int t = ky * d->kw + kx;
+            oy[t] = ky - d->pad; ox[t] = kx - d->pad; tix[t] = t;
+        }
+    return d->kh * d->kw;
+}
+static int dgrad_taps(const ccb_conv_desc* d, int py, int px, int* oy, int* ox, int* tix) {
+    const int s = d->stride;
+    int nt = 0;
+    for (int ky = 0; ky < d->kh; ++ky) {
+        if ((py + d->pad - ky) % s != 0) continue;
+        for (int kx = 0; kx < d->kw; ++kx) {
+            if ((px + d->pad - kx) % s != 0) continue;
+            oy[nt] = (py + d->pad - ky) / s; ox[nt] = (px + d->pad - kx) / s; tix[nt] = ky * d->kw + kx;
+            ++nt;
+        }
+    }
+    return nt;
+}
+// a tap list whose column offsets are all multiples of 4 pixels can be fetched tap by tap (conv_tma_kernel);
+// anything else goes through the slab kernel
+static bool taps_aligned(const int* ox, int nt, int in_stride, int Cc) {
+    if (in_stride != 1 || Cc < 8) return false;
+    for (int t = 0; t < nt; ++t)
+        if (ox[t] & 3) return false;
+    return true;
+}
+
+// Which problems the TMA-fed kernels take: 16-byte aligned rows of the gathered tensor, at least one full 32-column tile.
+bool tma_conv_supported(const ccb_conv_desc* d, int op) {
+    if (!g_tma_enabled || get_encode() == nullptr) return false;
+    if (d->kh != d->kw || d->kh * d->kw > TM_MAX_SLOTS) return false;
+    if (op == CCB_CONV_FPROP) return (d->stride == 1 || d->stride == 2) && (d->Wi % 4 == 0) && d->Wo >= 32;
+    if (op == CCB_CONV_DGRAD) return (d->Wo % 4 == 0) && cdiv(d->Wi, d->stride) >= 32;
+    return false;
+}
+
+static long long tma_wp_floats(const int* oy, const int* ox, int nt, int in_stride, int Cc, int N) {
+    if (taps_aligned(ox, nt, in_stride, Cc)) {
+        const int cb = Cc >= 32 ? 32 : (Cc > 8 ? 16 : 8);
+        const int Kp = cdiv((nt > 0 ? nt : 1) * cdiv(Cc, cb) * cb, 32) * 32;
+        return 2ll * N * Kp;
+    }
+    const SlabPlan p = slab_plan(oy, ox, nt, in_stride, Cc, N, 1);
+    return p.ok ? 2ll * N * p.ktiles * 32 : -1;
+}
+
+long long tma_workspace_floats(const ccb_conv_desc* d, int op) {
+    int oy[TM_MAX_SLOTS], ox[TM_MAX_SLOTS], tix[TM_MAX_SLOTS];
+    long long wpf = 0, tiles, out_numel;
+    if (op == CCB_CONV_FPROP) {
+        const int nt = fprop_taps(d, oy, ox, tix);
+        wpf = tma_wp_floats(oy, ox, nt, d->stride, d->Ci, d->Co);
+        tiles = (long long)d->B * cdiv(d->Wo, 32) * cdiv(d->Ho, 4) * cdiv(d->Co, 128);
+        out_numel = (long long)d->B * d->Co * d->Ho * d->Wo;
+    } else {
+        const int s = d->stride;
+        for (int py = 0; py < s && py < d->Hi; ++py)
+            for (int px = 0; px < s && px < d->Wi; ++px) {
+                const int nt = dgrad_taps(d, py, px, oy, ox, tix);
+                const long long f = tma_wp_floats(oy, ox, nt, 1, d->Co, d->Ci);
+                if (f < 0) return -1;
+                if (f > wpf) wpf = f;
+            }
+        tiles = (long long)d->B * cdiv(cdiv(d->Wi, s), 32) * cdiv(cdiv(d->Hi, s), 4) * cdiv(d->Ci, 128);
+        out_numel = (long long)d->B * d->Ci * d->Hi * d->Wi;
+    }
+    if (wpf < 0) return -1;
+    return wpf + (tiles < 148 ? 8 * out_numel : 0);      // weights + room for up to 8 split-K partials
+}
+
+static int tma_plan_splits(long long tiles, int ktiles, long long out_numel, long long part_floats) {
+    if (tiles >= 148 || ktiles < 4) return 1;
+    long long s = (2 * 148 + tiles - 1) / tiles;
+    if (s > ktiles / 2) s = ktiles / 2;
+    if (s > 8) s = 8;
+    if (out_numel > 0 && s * out_numel > part_floats) s = part_floats / out_numel;
+    return s < 2 ? 1 : (int)s;
+}
+
+// one launch of whichever kernel fits the tap list
+static int launch_any(const float* x, int B, int Cc, int Hin, int Win, const float* w, int mode, int N, int KK, int Ci,
+                      const int* oy, const int* ox, const int* tix, int nt, int in_stride, int Hc, int Wc, int Hout, int Wout,
+                      int out_stride, int out_oy, int out_ox, const float* bias, const float* res, float* out, int act, float slope,
+                      int three, float* work, long long wp_floats, int splits, float* partial, long long out_numel, cudaStream_t st) {
+    if (taps_aligned(ox, nt, in_stride, Cc))
+        return launch_tma(x, B, Cc, Hin, Win, w, mode, N, KK, Ci, oy, ox, tix, nt, Hc, Wc, Hout, Wout, out_stride, out_oy, out_ox, bias,
+                          res, out, act, slope, three, work, wp_floats, splits, partial, out_numel, st);
+    return launch_slab(x, B, Cc, Hin, Win, w, mode, N, KK, Ci, oy, ox, tix, nt, in_stride, Hc, Wc, Hout, Wout, out_stride, out_oy,
+                       out_ox, bias, res, out, act, slope, three, work, wp_floats, splits, partial, out_numel, st);
+}
+
+int tma_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float* bias, const float* res, float* y, float* work,
+              long long work_floats, int three, cudaStream_t st) {
+    int oy[TM_MAX_SLOTS], ox[TM_MAX_SLOTS], tix[TM_MAX_SLOTS];
+    const int nt = fprop_taps(d, oy, ox, tix);
+    const long long out_numel = (long long)d->B * d->Co * d->Ho * d->Wo;
+    const long long wpf = tma_wp_floats(oy, ox, nt, d->stride, d->Ci, d->Co);
+    CCB_REQUIRE(wpf >= 0 && wpf <= work_floats, CCB_ERR_ARG, "conv_tma fprop: workspace too small");
+    const long long tiles = (long long)d->B * cdiv(d->Wo, 32) * cdiv(d->Ho, 4) * cdiv(d->Co, 128);
+    const int splits = tma_plan_splits(tiles, (int)(wpf / (64ll * d->Co)), out_numel, work_floats - wpf);
+    int rc = launch_any(x, d->B, d->Ci, d->Hi, d->Wi, w, 0, d->Co, nt, d->Ci, oy, ox, tix, nt, d->stride, d->Ho, d->Wo, d->Ho, d->Wo, 1,
+                        0, 0, bias, res, y, d->act, d->slope, three, work, wpf, splits, work + wpf, out_numel, st);
+    if (rc || splits == 1) return rc;
+    launch_splitk_reduce(work + wpf, y, bias, res, out_numel, splits, d->Ho * d->Wo, d->Co, d->act, d->slope, st);
+    return check_launch("conv_tma splitk reduce");
+}
+
+int tma_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const float* bias, const float* res, float* dx, float* work,
+              long long work_floats, int three, cudaStream_t st) {
+    const int s = d->stride;
+    const long long out_numel = (long long)d->B * d->Ci * d->Hi * d->Wi;
+    int oy[TM_MAX_SLOTS], ox[TM_MAX_SLOTS], tix[TM_MAX_SLOTS];
+    long long wpf_max = 0;
+    for (int py = 0; py < s && py < d->Hi; ++py)
+        for (int px = 0; px < s && px < d->Wi; ++px) {
+            const int nt = dgrad_taps(d, py, px, oy, ox, tix);
+            const long long f = tma_wp_floats(oy, ox, nt, 1, d->Co, d->Ci);
+            CCB_REQUIRE(f >= 0, CCB_ERR_UNSUPPORTED, "conv_tma dgrad: no tiling");
+            if (f > wpf_max) wpf_max = f;
+        }
+    CCB_REQUIRE(wpf_max <= work_floats, CCB_ERR_ARG, "conv_tma dgrad: workspace too small");
+    const long long tiles = (long long)d->B * cdiv(cdiv(d->Wi, s), 32) * cdiv(cdiv(d->Hi, s), 4) * cdiv(d->Ci, 128);
+    const int splits = tma_plan_splits(tiles, (int)(wpf_max / (64ll * d->Ci)), out_numel, work_floats - wpf_max);
+    for (int py = 0; py < s && py < d->Hi; ++py)
+        for (int px = 0; px < s && px < d->Wi; ++px) {
+            const int nt = dgrad_taps(d, py, px, oy, ox, tix);
+            const int Hc = (d->Hi - py + s - 1) / s, Wc = (d->Wi - px + s - 1) / s;
+            int rc = launch_any(dy, d->B, d->Co, d->Ho, d->Wo, w, 1, d->Ci, d->kh * d->kw, d->Ci, oy, ox, tix, nt, 1, Hc, Wc, d->Hi, d->Wi,
+                                s, py, px, bias, res, dx, d->act, d->slope, three, work, wpf_max, splits, work + wpf_max, out_numel, st);
+            if (rc) return rc;
+        }
+    if (splits > 1) {
+        launch_splitk_reduce(work + wpf_max, dx, bias, res, out_numel, splits, d->Hi * d->Wi, d->Ci, d->act, d->slope, st);
+        return check_launch("conv_tma dgrad splitk reduce");
+    }
+    return CCB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// WGRAD: dw[co][ci][ky][kx] = sum over (b, oy, ox) of dy[b,co,oy,ox] * x[b,ci,oy*s+ky-p, ox*s+kx-p]
+//   GEMM with K = output pixels, one k-stage = 32 pixels of one output row:
+//     B: one TMA box (32 px, 1 row, n channels) of dy - K-major SWIZZLE_128B as it lands; the cutters add its
+//        tf32 remainder right behind it, so that [B_hi | B_lo] is one 2n-wide operand;
+//     A: rows = (tap, input channel) pairs of this CTA's M tile.  The input rows under those taps arrive as one
+//        aligned slab box; the cutters copy the tap-shifted 32-pixel runs into the K-major operand tile (value and
+//        remainder).  Zero padding and row tails are the TMA's OOB fill.
+//   D[(tap, ci)][co] accumulates in TMEM over this CTA's share of the pixels; split partials are summed in a fixed
+//   order by tma_splitk_sum_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+struct SlabWgradArgs {
+    int B, Ci, Co, Ho, Wo, KK, kw;
+    int stride, pad;
+    int cwid, cblocks, tpt, tgroups;       // channels per M tile, channel blocks, taps per M tile, tap groups
+    int SW, SH, slab_bytes, slab_tx, dx0;
+    int segs, stages, per_split, splits;
+    int nbox, nstages, soft;
+    long long numel;
+    float* out;
+};
+
+template <bool THREE>
+__global__ void __launch_bounds__(TM_THREADS, 1)
+conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const SlabWgradArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    const int NST = a.nstages;
+    const int b_bytes = (THREE ? 2 : 1) * a.nbox * 128;
+    const int ab_bytes = (THREE ? 2 : 1) * TM_A_BYTES + b_bytes;              // [A hi | A lo] [B hi ; B lo]
+    const int stage_bytes = ab_bytes + a.slab_bytes;                           // ... [slab]
+    uint64_t* bars = (uint64_t*)(smem + NST * stage_bytes);
+    uint64_t* tma_full = bars;           // [8] slab + dy box
+    uint64_t* a_full = bars + 8;         // [8] 256 cutter threads
+    uint64_t* empty_bar = bars + 16;     // [8] tcgen05.commit
+    uint64_t* accum_bar = bars + 24;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 25);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tg = blockIdx.x / a.cblocks, cblock = blockIdx.x - tg * a.cblocks;
+    const int n0 = blockIdx.y * 128;
+    const int ntile = min(128, a.Co - n0);
+    const int st_beg = blockIdx.z * a.per_split;
+    const int nst = max(0, min(a.stages, st_beg + a.per_split) - st_beg);
+    const int tap0 = tg * a.tpt;
+    const int ntap = min(a.tpt, a.KK - tap0);                                  // taps of this tile
+    const int c0 = cblock * a.cwid;
+    const int nch = min(a.cwid, a.Ci - c0);
+    const int ky_lo = tap0 / a.kw;
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) {
+            tm_mbar_init(&tma_full[s], 1);
+            tm_mbar_init(&a_full[s], 256);
+            tm_mbar_init(&empty_bar[s], 1);
+        }
+        tm_mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // operand rows without a (tap, channel) behind them stay zero for the whole launch
+    for (int s = 0; s < NST; ++s) {
+        float4* p = (float4*)(smem + s * stage_bytes);
+        for (int i = tid; i < (THREE ? 2048 : 1024); i += TM_THREADS) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx_bytes = (uint32_t)(a.slab_tx + a.nbox * 128);
+            const int per_img = a.Ho * a.segs;
+            int g = st_beg;
+            int b = g / per_img;
+            int r = g - b * per_img;
+            int oy = r / a.segs, seg = r - oy * a.segs;
+            for (int it = 0; it < nst; ++it) {
+                const int s = it % NST;
+                if (it >= NST) tm_mbar_wait(&empty_bar[s], ((it / NST) - 1) & 1, a.soft, 1, it);
+                unsigned char* st = smem + s * stage_bytes;
+                tm_mbar_expect_tx(&tma_full[s], tx_bytes);
+                tma_load_4d(st + ab_bytes, &map_x, &tma_full[s], seg * 32 * a.stride - a.pad - a.dx0, oy * a.stride + ky_lo - a.pad, c0, b);
+                tma_load_4d(st + (THREE ? 2 : 1) * TM_A_BYTES, &map_dy, &tma_full[s], seg * 32, oy, n0, b);
+                if (++seg == a.segs) { seg = 0; if (++oy == a.Ho) { oy = 0; ++b; } }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TM_M >> 4) << 24);
+        const uint32_t idesc_n1 = idesc_base | ((uint32_t)(a.nbox >> 3) << 17);
+        const uint32_t idesc_n2 = idesc_base | ((uint32_t)((2 * a.nbox) >> 3) << 17);
+        for (int it = 0; it < nst; ++it) {
+            const int s = it % NST;
+            tm_mbar_wait(&a_full[s], (it / NST) & 1, a.soft, 3, it);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t st = smem_addr(smem + s * stage_bytes);
+                const uint32_t a_hi = st, a_lo = st + TM_A_BYTES;
+                const uint32_t bt = st + (THREE ? 2 : 1) * TM_A_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t ah = tm_desc(a_hi + ks * 32, 16, 1024, 2);
+                    const uint64_t bh = tm_desc(bt + ks * 32, 16, 1024, 2);
+                    const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+                    tm_umma_tf32(tmem_base, ah, bh, THREE ? idesc_n2 : idesc_n1, acc);
+                    if (THREE) {
+                        const uint64_t al = tm_desc(a_lo + ks * 32, 16, 1024, 2);
+                        tm_umma_tf32(tmem_base + 256u, al, bh, idesc_n1, acc);
+                    }
+                }
+                tm_commit(&empty_bar[s]);
+                if (it == nst - 1) tm_commit(accum_bar);
+            }
+            __syncwarp();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        const int w8 = warp - 2, wt = tid - 64;
+        // this thread's 16 operand rows: row = w8 * 16 + j -> (tap, channel) -> slab offset of pixel 0 (or -1)
+        int roff[16];
+        const int plane = a.SH * a.SW;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int r = w8 * 16 + j;
+            const int tl = r / a.cwid, c = r - tl * a.cwid;
+            const int tap = tap0 + tl;
+            const int ky = tap / a.kw, kx = tap - ky * a.kw;
+            roff[j] = (tl < ntap && c < nch) ? c * plane + (ky - ky_lo) * a.SW + a.dx0 + kx + lane * a.stride : -1;
+        }
+        const int b4 = a.nbox * 8;                                             // float4 of the dy tile
+        for (int it = 0; it < nst; ++it) {
+            const int s = it % NST;
+            tm_mbar_wait(&tma_full[s], (it / NST) & 1, a.soft, 4, it);
+            unsigned char* st = smem + s * stage_bytes;
+            const float* slab = (const float*)(st + ab_bytes);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (roff[j] >= 0) {
+                    const int r = w8 * 16 + j;
+                    const float v = slab[roff[j]];
+                    const uint32_t dst = (uint32_t)(r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+                    *(float*)(st + dst) = v;
+                    if (THREE) *(float*)(st + TM_A_BYTES + dst) = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                }
+            }
+            if (THREE) {
+                float4* braw = (float4*)(st + 2 * TM_A_BYTES);
+                float4* blo = braw + b4;
+                for (int i = wt; i < b4; i += 256) {
+                    float4 v = braw[i], l;
+                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    blo[i] = l;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tm_mbar_arrive(&a_full[s]);
+        }
+        if (nst > 0) tm_mbar_wait(accum_bar, 0, a.soft, 5, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q4 = warp & 3, colhalf = (warp - 2) >> 2;
+        const int m = q4 * 32 + lane;                       // TMEM lane = operand row = (tap, channel)
+        const int tl = m / a.cwid, cl = m - tl * a.cwid;
+        const int tap = tap0 + tl, c = c0 + cl;
+        const bool rvalid = (tl < ntap) && (cl < nch);
+        float* outp = a.out + (long long)blockIdx.z * a.numel;
+        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        for (int cg = colhalf; cg * 16 < ntile; cg += 2) {
+            float v[16];
+            if (nst > 0) {
+                tm_ld16(trow + (uint32_t)(cg * 16), v);
+                if (THREE) {
+                    float v2[16];
+                    tm_ld16(trow + (uint32_t)(a.nbox + cg * 16), v2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                    tm_ld16(trow + 256u + (uint32_t)(cg * 16), v2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+            if (rvalid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int co = n0 + cg * 16 + j;
+                    if (cg * 16 + j < ntile) outp[((long long)co * a.Ci + c) * a.KK + tap] = v[j];
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(256) tma_splitk_sum_kernel(const float* __restrict__ work, float* __restrict__ out, long long numel,
+                                                             int splits) {
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= numel) return;
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += __ldg(work + (long long)s * numel + i);
+    out[i] = v;
+}
+
+static bool wgrad_plan(const ccb_conv_desc* d, int three, SlabWgradArgs& a, int& smem) {
+    const int KK = d->kh * d->kw;
+    a.cwid = d->Ci < 128 ? d->Ci : 128;
+    a.cblocks = cdiv(d->Ci, a.cwid);
+    const int tpt_max = 128 / a.cwid;
+    a.tgroups = cdiv(KK, tpt_max);
+    a.tpt = cdiv(KK, a.tgroups);                           // balanced tap groups
+    // input rows under one tap group
+    int sh = 1;
+    for (int g = 0; g < a.tgroups; ++g) {
+        const int t0 = g * a.tpt, t1 = (t0 + a.tpt < KK ? t0 + a.tpt : KK) - 1;
+        const int span = t1 / d->kw - t0 / d->kw + 1;
+        if (span > sh) sh = span;
+    }
+    a.SH = sh;
+    a.dx0 = ((-d->pad) % 4 + 4) % 4;                       // column of tap kx = 0, pixel 0 inside the aligned slab
+    a.SW = (31 * d->stride + d->kw + a.dx0 + 3) & ~3;
+    a.slab_tx = a.cwid * a.SH * a.SW * 4;
+    a.slab_bytes = cdiv(a.slab_tx, 1024) * 1024;
+    const int ntile = d->Co < 128 ? d->Co : 128;
+    a.nbox = (ntile + 15) & ~15;
+    const int stage = (three ? 2 : 1) * (TM_A_BYTES + a.nbox * 128) + a.slab_bytes;
+    a.nstages = (224 * 1024) / stage;
+    if (a.nstages > 6) a.nstages = 6;
+    if (a.nstages < 2 || a.SW > 256 || a.cwid > 256) return false;
+    smem = a.nstages * stage + 512 + 1024;
+    a.segs = cdiv(d->Wo, 32);
+    a.stages = d->B * d->Ho * a.segs;
+    const int tiles = a.tgroups * a.cblocks * cdiv(d->Co, 128);
+    int splits = tiles >= 148 ? 1 : 148 / tiles;
+    if (splits > a.stages / 8) splits = a.stages / 8;
+    if (splits < 1) splits = 1;
+    a.per_split = cdiv(a.stages, splits);
+    a.splits = cdiv(a.stages, a.per_split);
+    return true;
+}
+
+bool tma_wgrad_supported(const ccb_conv_desc* d) {
+    if (!g_tma_enabled || get_encode() == nullptr) return false;
+    if (d->kh != d->kw || (d->stride != 1 && d->stride != 2)) return false;
+    if ((d->Wi % 4) || (d->Wo % 4) || d->Wo < 32) return false;
+    SlabWgradArgs a;
+    int smem;
+    return wgrad_plan(d, 1, a, smem);
+}
+long long tma_wgrad_workspace_floats(const ccb_conv_desc* d) {
+    SlabWgradArgs a;
+    int smem;
+    if (!wgrad_plan(d, 1, a, smem)) return 0;
+    return a.splits > 1 ? (long long)a.splits * d->Co * d->Ci * d->kh * d->kw : 0;
+}
+
+int tma_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw, float* work, long long work_floats, int three,
+              cudaStream_t st) {
+    EncodeTiledFn enc = get_encode();
+    CCB_REQUIRE(enc != nullptr, CCB_ERR_UNSUPPORTED, "conv_tma: cuTensorMapEncodeTiled unavailable");
+    SlabWgradArgs a;
+    memset(&a, 0, sizeof(a));
+    int smem = 0;
+    CCB_REQUIRE(wgrad_plan(d, three, a, smem), CCB_ERR_UNSUPPORTED, "conv_tma wgrad: no tiling fits shared memory");
+    a.B = d->B; a.Ci = d->Ci; a.Co = d->Co; a.Ho = d->Ho; a.Wo = d->Wo; a.KK = d->kh * d->kw; a.kw = d->kw;
+    a.stride = d->stride; a.pad = d->pad; a.soft = g_tma_soft;
+    a.numel = (long long)d->Co * d->Ci * a.KK;
+    if (a.splits > 1) {
+        CCB_REQUIRE(work && (long long)a.splits * a.numel <= work_floats, CCB_ERR_ARG, "conv_tma wgrad: workspace too small");
+        a.out = work;
+    } else {
+        a.out = dw;
+    }
+    alignas(64) CUtensorMap map_x, map_dy;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->Ci, (cuuint64_t)d->B};
+        cuuint64_t strides[3] = {(cuuint64_t)d->Wi * 4, (cuuint64_t)d->Wi * d->Hi * 4, (cuuint64_t)d->Wi * d->Hi * d->Ci * 4};
+        cuuint32_t box[4] = {(cuuint32_t)a.SW, (cuuint32_t)a.SH, (cuuint32_t)a.cwid, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CCB_REQUIRE(r == CUDA_SUCCESS, CCB_ERR_LAUNCH, "conv_tma wgrad: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)d->Wo, (cuuint64_t)d->Ho, (cuuint64_t)d->Co, (cuuint64_t)d->B};
+        cuuint64_t strides[3] = {(cuuint64_t)d->Wo * 4, (cuuint64_t)d->Wo * d->Ho * 4, (cuuint64_t)d->Wo * d->Ho * d->Co * 4};
+        cuuint32_t box[4] = {32, 1, (cuuint32_t)a.nbox, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map_dy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)dy, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CCB_REQUIRE(r == CUDA_SUCCESS, CCB_ERR_LAUNCH, "conv_tma wgrad: cuTensorMapEncodeTiled(dy) failed (%d)", (int)r);
+    }
+    dim3 grid(a.tgroups * a.cblocks, cdiv(d->Co, 128), a.splits);
+    auto kfn = three ? conv_slab_wgrad_kernel<true> : conv_slab_wgrad_kernel<false>;
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    CCB_LAUNCH(kfn, grid, dim3(TM_THREADS), smem, st, map_x, map_dy, a);
+    int rc = check_launch("conv_slab_wgrad");
+    if (rc || a.splits == 1) return rc;
+    CCB_LAUNCH(tma_splitk_sum_kernel, dim3((unsigned)((a.numel + 255) / 256)), dim3(256), 0, st, (const float*)work, dw, a.numel, a.splits);
+    return check_launch("conv_slab_wgrad_reduce");
+}
+
+}  // namespace ccb
+
+extern "C" int ccb_debug_tma_status(unsigned int* out4) {
+    if (!out4) return CCB_ERR_ARG;
+    unsigned int zero[4] = {0, 0, 0, 0};
+    if (cudaDeviceSynchronize() != cudaSuccess) return CCB_ERR_LAUNCH;
+    if (cudaMemcpyFromSymbol(out4, ccb::g_tma_status, sizeof(zero)) != cudaSuccess) return CCB_ERR_LAUNCH;
+    if (cudaMemcpyToSymbol(ccb::g_tma_status, zero, sizeof(zero)) != cudaSuccess) return CCB_ERR_LAUNCH;
+    return CCB_OK;
+}
+
+#else
+
+namespace ccb {
+void tma_set_enabled(int) {}
+bool tma_conv_supported(const ccb_conv_desc*, int) { return false; }
+long long tma_workspace_floats(const ccb_conv_desc*, int) { return 0; }
+int tma_fprop(const ccb_conv_desc*, const float*, const float*, const float*, const float*, float*, float*, long long, int,
+              cudaStream_t) { return CCB_ERR_UNSUPPORTED; }
+int tma_dgrad(const ccb_conv_desc*, const float*, const float*, const float*, const float*, float*, float*, long long, int,
+              cudaStream_t) { return CCB_ERR_UNSUPPORTED; }
+bool tma_wgrad_supported(const ccb_conv_desc*) { return false; }
+long long tma_wgrad_workspace_floats(const ccb_conv_desc*) { return 0; }
+int tma_wgrad(const ccb_conv_desc*, const float*, const float*, float*, float*, long long, int, cudaStream_t) {
+    return CCB_ERR_UNSUPPORTED;
+}
+}  // namespace ccb
+extern "C" int ccb_debug_tma_status(unsigned int* out4) {
+    if (out4) out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    return CCB_OK;
+}
+
+#endif

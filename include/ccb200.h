@@ -227,8 +227,14 @@ int ccb_act_bwd(const float* dy, const float* y, float* dz, long long numel, int
 int ccb_bias_grad(const float* dy, float* db, int B, int C, int plane, ccb_stream_t stream);
 /* bring-up aid (layout probe): bit 0 swaps the LBO/SBO strides of the UMMA shared-memory descriptors
  * (must produce wrong results), bit 2 selects the K-major no-swizzle operand layout instead of the
- * default SWIZZLE_128B one (must produce identical results) */
+ * default SWIZZLE_128B one (must produce identical results), bit 3 turns the TMA-fed kernels off so that
+ * every shape takes the register-gather tensor-core kernels (must produce results within rounding), bit 4 makes
+ * a barrier time-out inside the TMA kernels a recorded event instead of a trap */
 void ccb_debug_tc_swap_strides(int swap);
+/* synchronises the device, then returns and clears the first recorded barrier time-out of the TMA conv kernels:
+ * out4 = {role (0 = none; 1 producer/empty, 2 mma/tma_full, 3 mma/split_full, 4 split/tma_full, 5 epilogue/accum),
+ * k-iteration, blockIdx.x, blockIdx.z} */
+int ccb_debug_tma_status(unsigned int* out4);
 
 /* Back2Future operators (models/back2future.py).
  * corr81: cost volume of correlate() :15-25 (third-party spatial_correlation_sample, kernel 1, patch 9,

@@ -21,7 +21,8 @@
 namespace ccb {
 
 constexpr int TM_M = 128;
-constexpr int TM_THREADS = 320;            // warp 0: TMA, warp 1: MMA + TMEM, warps 2..9: lo-pass + epilogue
+constexpr int TM_THREADS = 320;            // direct kernel: warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 lo-pass + epilogue
+constexpr int SL_THREADS = 576;            // slab kernels: warp 0 TMA, warp 1 MMA + TMEM, two groups of 8 cutter warps
 constexpr int TM_MAX_SLOTS = 64;           // tap slots (taps padded to a multiple of 32/cb)
 constexpr int TM_A_BYTES = 16384;          // one A operand copy of one stage: 128 px x 32 k x 4 B
 
@@ -131,6 +132,23 @@ __device__ __forceinline__ uint64_t tm_desc(uint32_t saddr, uint32_t lbo_bytes, 
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)layout << 61;
     return d;
+}
+// four consecutive floats starting `al` (0..3) floats past the 16-byte aligned address p
+__device__ __forceinline__ float4 ld_shift4(const float* p, int al) {
+    const float4 a = *(const float4*)p;
+    if (al == 0) return a;
+    const float4 b = *(const float4*)(p + 4);
+    if (al == 1) return make_float4(a.y, a.z, a.w, b.x);
+    if (al == 2) return make_float4(a.z, a.w, b.x, b.y);
+    return make_float4(a.w, b.x, b.y, b.z);
+}
+__device__ __forceinline__ float4 tf32_rest4(const float4 v) {
+    float4 l;
+    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    return l;
 }
 __device__ __forceinline__ float tm_act(float v, int act, float slope) {
     switch (act) {
@@ -483,7 +501,7 @@ struct SlabArgs {
 };
 
 template <bool THREE>
-__global__ void __launch_bounds__(TM_THREADS, 1)
+__global__ void __launch_bounds__(SL_THREADS, 1)
 conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b, const SlabArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
@@ -491,13 +509,14 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int stage_bytes = (THREE ? 2 : 1) * TM_A_BYTES + a.b_tile_bytes;     // [A hi | A lo] [B hi ; B lo]
     unsigned char* slab0 = smem + NST * stage_bytes;
     uint64_t* bars = (uint64_t*)(slab0 + a.nslab * a.slab_bytes);
-    uint64_t* a_full = bars;             // [8]  256 cutter threads
+    uint64_t* a_full = bars;             // [8]  the 8 cutter warps of one group
     uint64_t* b_full = bars + 8;         // [8]  TMA weights
     uint64_t* empty_bar = bars + 16;     // [8]  tcgen05.commit
     uint64_t* slab_full = bars + 24;     // [2]  TMA slab
-    uint64_t* slab_empty = bars + 26;    // [2]  256 cutter threads
+    uint64_t* slab_empty = bars + 26;    // [2]  16 cutter warps
     uint64_t* accum_bar = bars + 28;
     uint32_t* tmem_slot = (uint32_t*)(bars + 29);
+    int* toff = (int*)(bars + 32);       // [64] slab offset of each tap
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int t = blockIdx.x;
@@ -516,15 +535,19 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int ys = y0 * s_in + a.oy_lo;
     const int first_block = min(kt_beg / a.kt_full, a.cblocks - 1);
 
+    if (tid >= 64 && tid < 64 + TM_MAX_SLOTS) {
+        const int tp = tid - 64;
+        toff[tp] = (tp < a.ntaps) ? (a.off_y[tp] - a.oy_lo) * a.SW + (a.off_x[tp] - a.ox_lo) : 0;
+    }
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) {
-            tm_mbar_init(&a_full[s], 256);
+            tm_mbar_init(&a_full[s], 8);
             tm_mbar_init(&b_full[s], 1);
             tm_mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             tm_mbar_init(&slab_full[s], 1);
-            tm_mbar_init(&slab_empty[s], 256);
+            tm_mbar_init(&slab_empty[s], 16);
         }
         tm_mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -595,51 +618,105 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
-        // ===================== cutters (8 warps): slab -> operand tiles; then the epilogue =====================
-        const int w8 = warp - 2;                               // this warp owns k rows 4*w8 .. 4*w8+3 of every stage
+        // ===================== cutters (2 groups of 8 warps): slab -> operand tiles; then the epilogue =====================
+        // The groups take alternate k-stages, so two stages are being cut at any time (one stage is a chain of
+        // shared-memory round trips, not a throughput problem).  Inside a group warp w8 owns k rows 4*w8 .. 4*w8+3;
+        // a quarter warp writes one 128-byte operand row: lane -> (tile row mb, group of 4 pixels).
+        const int grp = (warp - 2) >> 3, w8 = (warp - 2) & 7;
+        const int pxg = lane & 7, mb = lane >> 3;
         const int plane = a.SH * a.SW;
+        const int thr_off = mb * s_in * a.SW + pxg * 4 * s_in + dx0;           // this thread's corner inside a slab plane
+        uint32_t dst[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = w8 * 4 + i;
+            dst[i] = (uint32_t)(mb * 4096 + k * 128 + (((pxg >> 1) ^ (k & 3)) << 5) + (pxg & 1) * 16);
+        }
+        int cblock = first_block, q = 0;
+        int kl_stage = kt_beg - cblock * a.kt_full;                             // k-stage inside the block
+        int blk_stages = (cblock < a.cblocks - 1) ? a.kt_full : a.ktiles - (a.cblocks - 1) * a.kt_full;
+        int nch = min(a.cs, a.Cin - cblock * a.cs);
+        int q32 = 32 / nch, r32 = 32 - q32 * nch;
+        int tap0 = (kl_stage * 32 + w8 * 4) / nch, c0 = (kl_stage * 32 + w8 * 4) - tap0 * nch;
+        bool need_slab = true;                                                  // this warp has not looked at the current slab yet
         for (int it = 0; it < ktiles; ++it) {
-            const int kt = kt_beg + it;
-            const int cblock = min(kt / a.kt_full, a.cblocks - 1);
-            const int q = cblock - first_block;
-            const float* slab = (const float*)(slab0 + (q % a.nslab) * a.slab_bytes);
-            const bool first_of_block = (it == 0) || (min((kt - 1) / a.kt_full, a.cblocks - 1) != cblock);
-            const bool last_of_block = (it == ktiles - 1) || (min((kt + 1) / a.kt_full, a.cblocks - 1) != cblock);
-            if (first_of_block) tm_mbar_wait(&slab_full[q % a.nslab], (q / a.nslab) & 1, a.soft, 4, it);
-            const int s = it % NST;
-            if (it >= NST) tm_mbar_wait(&empty_bar[s], ((it / NST) - 1) & 1, a.soft, 7, it);
-            unsigned char* st = smem + s * stage_bytes;
-            const int nch = min(a.cs, a.Cin - cblock * a.cs);
-            int kl = (kt - cblock * a.kt_full) * 32 + w8 * 4;      // flattened (tap, channel) index inside the block
-            int tap = kl / nch, c = kl - tap * nch;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int k = w8 * 4 + i;
-                const bool kvalid = tap < a.ntaps;
-                const int src = kvalid ? c * plane + (a.off_y[tap] - a.oy_lo) * a.SW + (a.off_x[tap] - a.ox_lo) + dx0 + lane * s_in : 0;
-                const uint32_t dst = (uint32_t)(k * 128 + ((((lane >> 3) ^ (k & 3))) << 5) + (lane & 7) * 4);
-#pragma unroll
-                for (int mb = 0; mb < 4; ++mb) {
-                    const float v = kvalid ? slab[src + mb * s_in * a.SW] : 0.f;
-                    *(float*)(st + mb * 4096 + dst) = v;
-                    if (THREE) *(float*)(st + TM_A_BYTES + mb * 4096 + dst) = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            const int sb = q % a.nslab;
+            if ((it & 1) == grp) {
+                const float* slab = (const float*)(slab0 + sb * a.slab_bytes);
+                if (need_slab) {
+                    tm_mbar_wait(&slab_full[sb], (q / a.nslab) & 1, a.soft, 4, it);
+                    need_slab = false;
                 }
-                if (++c == nch) { c = 0; ++tap; }
+                const int s = it % NST;
+                if (it >= NST) tm_mbar_wait(&empty_bar[s], ((it / NST) - 1) & 1, a.soft, 7, it);
+                unsigned char* st = smem + s * stage_bytes;
+                int sidx[4];
+                bool kval[4];
+                {
+                    int tap = tap0, c = c0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        kval[i] = tap < a.ntaps;
+                        sidx[i] = thr_off + (kval[i] ? c * plane + toff[tap] : 0);
+                        if (++c == nch) { c = 0; ++tap; }
+                    }
+                }
+                float4 v[4];
+                if (s_in == 1) {
+                    float4 va[4], vb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) va[i] = *(const float4*)(slab + (sidx[i] & ~3));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vb[i] = *(const float4*)(slab + (sidx[i] & ~3) + 4);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int al = sidx[i] & 3;
+                        v[i] = al == 0 ? va[i]
+                             : al == 1 ? make_float4(va[i].y, va[i].z, va[i].w, vb[i].x)
+                             : al == 2 ? make_float4(va[i].z, va[i].w, vb[i].x, vb[i].y)
+                                       : make_float4(va[i].w, vb[i].x, vb[i].y, vb[i].z);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[i].x = slab[sidx[i]]; v[i].y = slab[sidx[i] + s_in];
+                        v[i].z = slab[sidx[i] + 2 * s_in]; v[i].w = slab[sidx[i] + 3 * s_in];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (!kval[i]) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *(float4*)(st + dst[i]) = v[i];
+                    if (THREE) *(float4*)(st + TM_A_BYTES + dst[i]) = tf32_rest4(v[i]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tm_mbar_arrive(&a_full[s]);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            tm_mbar_arrive(&a_full[s]);
-            if (last_of_block) tm_mbar_arrive(&slab_empty[q % a.nslab]);
+            ++kl_stage;
+            const bool block_done = (kl_stage == blk_stages);
+            if ((block_done || it == ktiles - 1) && lane == 0) tm_mbar_arrive(&slab_empty[sb]);
+            if (block_done && it + 1 < ktiles) {
+                ++cblock; ++q; kl_stage = 0; need_slab = true;
+                blk_stages = (cblock < a.cblocks - 1) ? a.kt_full : a.ktiles - (a.cblocks - 1) * a.kt_full;
+                nch = min(a.cs, a.Cin - cblock * a.cs);
+                q32 = 32 / nch; r32 = 32 - q32 * nch;
+                tap0 = (w8 * 4) / nch; c0 = (w8 * 4) - tap0 * nch;
+            } else {
+                c0 += r32; tap0 += q32;
+                if (c0 >= nch) { c0 -= nch; ++tap0; }
+            }
         }
         if (ktiles > 0) tm_mbar_wait(accum_bar, 0, a.soft, 5, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q4 = warp & 3, colhalf = (warp - 2) >> 2;
+        const int q4 = warp & 3, colq = (warp - 2) >> 2;        // 4 warps per TMEM lane quarter split the columns
         const int oy = y0 + q4, ox = x0 + lane;
         const bool evalid = (oy < a.Hc) && (ox < a.Wc);
         const long long HWout = (long long)a.Hout * a.Wout;
         const long long obase = (long long)b * a.Ntot * HWout + (long long)(oy * a.out_stride + a.out_oy) * a.Wout +
                                 (ox * a.out_stride + a.out_ox);
         const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
-        for (int cg = colhalf; cg * 16 < ntile; cg += 2) {
+        for (int cg = colq; cg * 16 < ntile; cg += 4) {
             float v[16];
             if (ktiles > 0) {
                 tm_ld16(trow + (uint32_t)(cg * 16), v);
@@ -738,7 +815,7 @@ static SlabPlan slab_plan(const int* off_y, const int* off_x, int ntaps, int in_
     int g = nt, r = 32;                    // channel granularity that makes cs * ntaps a multiple of 32
     while (r) { int q = g % r; g = r; r = q; }
     const int align = 32 / g;
-    const int total = 225 * 1024;
+    const int total = 224 * 1024;
     for (int nst = 3; nst >= 2 && !p.ok; --nst) {
         const int budget = total - nst * stage;
         for (int cb = 1; cb <= Cc && !p.ok; ++cb) {
@@ -759,7 +836,7 @@ static SlabPlan slab_plan(const int* off_y, const int* off_x, int ntaps, int in_
     p.kt_full = cdiv(p.cs * nt, 32);
     const int tail = Cc - (p.cblocks - 1) * p.cs;
     p.ktiles = (p.cblocks - 1) * p.kt_full + cdiv(tail * nt, 32);
-    p.smem = p.nstages * stage + p.nslab * p.slab_bytes + 512 + 1024;
+    p.smem = p.nstages * stage + p.nslab * p.slab_bytes + 1024 + 1024;
     return p;
 }
 
@@ -820,7 +897,7 @@ static int launch_slab(const float* x, int B, int Cc, int Hin, int Win, const fl
     dim3 grid(B * a.tiles_x * a.tiles_y, cdiv(N, 128), splits);
     auto kfn = three ? conv_slab_kernel<true> : conv_slab_kernel<false>;
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    CCB_LAUNCH(kfn, grid, dim3(TM_THREADS), p.smem, st, map_x, map_b, a);
+    CCB_LAUNCH(kfn, grid, dim3(SL_THREADS), p.smem, st, map_x, map_b, a);
     return check_launch("conv_slab");
 }
 
@@ -989,7 +1066,7 @@ struct SlabWgradArgs {
 };
 
 template <bool THREE>
-__global__ void __launch_bounds__(TM_THREADS, 1)
+__global__ void __launch_bounds__(SL_THREADS, 1)
 conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const SlabWgradArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
@@ -1019,7 +1096,7 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) {
             tm_mbar_init(&tma_full[s], 1);
-            tm_mbar_init(&a_full[s], 256);
+            tm_mbar_init(&a_full[s], 8);
             tm_mbar_init(&empty_bar[s], 1);
         }
         tm_mbar_init(accum_bar, 1);
@@ -1032,7 +1109,7 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     // operand rows without a (tap, channel) behind them stay zero for the whole launch
     for (int s = 0; s < NST; ++s) {
         float4* p = (float4*)(smem + s * stage_bytes);
-        for (int i = tid; i < (THREE ? 2048 : 1024); i += TM_THREADS) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < (THREE ? 2048 : 1024); i += SL_THREADS) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1088,59 +1165,77 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
-        const int w8 = warp - 2, wt = tid - 64;
-        // this thread's 16 operand rows: row = w8 * 16 + j -> (tap, channel) -> slab offset of pixel 0 (or -1)
-        int roff[16];
+        // two groups of 8 cutter warps take alternate k-stages.  Inside a group warp w8 owns operand rows
+        // 16*w8 .. 16*w8+15; a quarter warp writes one 128-byte row (32 pixels): lane -> (row within a group of 4,
+        // group of 4 pixels).  Row -> (tap, channel) never changes.
+        const int grp = (warp - 2) >> 3, w8 = (warp - 2) & 7, wt = (tid - 64) & 255;
+        const int pxg = lane & 7, sub = lane >> 3;
         const int plane = a.SH * a.SW;
+        int ridx[4];
+        uint32_t rdst[4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int r = w8 * 16 + j;
+        for (int j = 0; j < 4; ++j) {
+            const int r = w8 * 16 + j * 4 + sub;
             const int tl = r / a.cwid, c = r - tl * a.cwid;
             const int tap = tap0 + tl;
             const int ky = tap / a.kw, kx = tap - ky * a.kw;
-            roff[j] = (tl < ntap && c < nch) ? c * plane + (ky - ky_lo) * a.SW + a.dx0 + kx + lane * a.stride : -1;
+            ridx[j] = (tl < ntap && c < nch) ? c * plane + (ky - ky_lo) * a.SW + a.dx0 + kx + pxg * 4 * a.stride : -1;
+            rdst[j] = (uint32_t)(r * 128 + ((pxg ^ (r & 7)) << 4));
         }
         const int b4 = a.nbox * 8;                                             // float4 of the dy tile
-        for (int it = 0; it < nst; ++it) {
+        for (int it = grp; it < nst; it += 2) {
             const int s = it % NST;
             tm_mbar_wait(&tma_full[s], (it / NST) & 1, a.soft, 4, it);
             unsigned char* st = smem + s * stage_bytes;
             const float* slab = (const float*)(st + ab_bytes);
+            float4 v[4];
+            if (a.stride == 1) {
+                float4 va[4], vb[4];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if (roff[j] >= 0) {
-                    const int r = w8 * 16 + j;
-                    const float v = slab[roff[j]];
-                    const uint32_t dst = (uint32_t)(r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
-                    *(float*)(st + dst) = v;
-                    if (THREE) *(float*)(st + TM_A_BYTES + dst) = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                for (int j = 0; j < 4; ++j) va[j] = *(const float4*)(slab + (max(ridx[j], 0) & ~3));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) vb[j] = *(const float4*)(slab + (max(ridx[j], 0) & ~3) + 4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int al = ridx[j] & 3;
+                    v[j] = al == 0 ? va[j]
+                         : al == 1 ? make_float4(va[j].y, va[j].z, va[j].w, vb[j].x)
+                         : al == 2 ? make_float4(va[j].z, va[j].w, vb[j].x, vb[j].y)
+                                   : make_float4(va[j].w, vb[j].x, vb[j].y, vb[j].z);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i0 = max(ridx[j], 0);
+                    v[j].x = slab[i0]; v[j].y = slab[i0 + a.stride]; v[j].z = slab[i0 + 2 * a.stride]; v[j].w = slab[i0 + 3 * a.stride];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (ridx[j] >= 0) {
+                    *(float4*)(st + rdst[j]) = v[j];
+                    if (THREE) *(float4*)(st + TM_A_BYTES + rdst[j]) = tf32_rest4(v[j]);
                 }
             }
             if (THREE) {
                 float4* braw = (float4*)(st + 2 * TM_A_BYTES);
                 float4* blo = braw + b4;
-                for (int i = wt; i < b4; i += 256) {
-                    float4 v = braw[i], l;
-                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                    blo[i] = l;
-                }
+                for (int i = wt; i < b4; i += 256) blo[i] = tf32_rest4(braw[i]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            tm_mbar_arrive(&a_full[s]);
+            __syncwarp();
+            if (lane == 0) tm_mbar_arrive(&a_full[s]);
         }
         if (nst > 0) tm_mbar_wait(accum_bar, 0, a.soft, 5, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q4 = warp & 3, colhalf = (warp - 2) >> 2;
+        const int q4 = warp & 3, colq = (warp - 2) >> 2;
         const int m = q4 * 32 + lane;                       // TMEM lane = operand row = (tap, channel)
         const int tl = m / a.cwid, cl = m - tl * a.cwid;
         const int tap = tap0 + tl, c = c0 + cl;
         const bool rvalid = (tl < ntap) && (cl < nch);
         float* outp = a.out + (long long)blockIdx.z * a.numel;
         const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
-        for (int cg = colhalf; cg * 16 < ntile; cg += 2) {
+        for (int cg = colq; cg * 16 < ntile; cg += 4) {
             float v[16];
             if (nst > 0) {
                 tm_ld16(trow + (uint32_t)(cg * 16), v);
@@ -1274,7 +1369,7 @@ int tma_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw
     dim3 grid(a.tgroups * a.cblocks, cdiv(d->Co, 128), a.splits);
     auto kfn = three ? conv_slab_wgrad_kernel<true> : conv_slab_wgrad_kernel<false>;
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    CCB_LAUNCH(kfn, grid, dim3(TM_THREADS), smem, st, map_x, map_dy, a);
+    CCB_LAUNCH(kfn, grid, dim3(SL_THREADS), smem, st, map_x, map_dy, a);
     int rc = check_launch("conv_slab_wgrad");
     if (rc || a.splits == 1) return rc;
     CCB_LAUNCH(tma_splitk_sum_kernel, dim3((unsigned)((a.numel + 255) / 256)), dim3(256), 0, st, (const float*)work, dw, a.numel, a.splits);

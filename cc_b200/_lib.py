@@ -103,7 +103,8 @@ _SIGS = {
     'ccb_conv2d_dgrad': (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _LL, _P]),
     'ccb_conv2d_wgrad': (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _LL, _P]),
     'ccb_act_bwd': (_I, [_P, _P, _P, _LL, _I, _F, _P]),
-    'ccb_bias_grad': (_I, [_P, _P, _I, _I, _I, _P]),
+    'ccb_bias_grad_workspace_floats': (_LL, [_I, _I, _I]),
+    'ccb_bias_grad': (_I, [_P, _P, _I, _I, _I, _P, _LL, _P]),
     'ccb_debug_tc_swap_strides': (None, [_I]),
     'ccb_debug_tma_status': (_I, [C.POINTER(C.c_uint)]),
     'ccb_corr81_fwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),

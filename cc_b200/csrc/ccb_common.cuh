@@ -36,6 +36,19 @@ int check_launch(const char* what);
         }                                       \
     } while (0)
 
+// ---- weight preparation for the tensor-core conv kernels (wprep.cu) ----
+enum { WPREP_TC = 0, WPREP_TMA = 1, WPREP_SLAB = 2 };
+struct WPrepDesc {
+    const float* w;
+    float* wp;
+    int N, Cc, KK, Ci, mode, Kp, ntaps;
+    int layout, p0, p1, p2;      // TC: p0 = cpad;  TMA: p0 = cb, p1 = cblocks, p2 = units;  SLAB: p0 = cs, p1 = cblocks, p2 = kt_full
+    signed char tap_index[64];
+};
+#ifndef CCB_CPU_SIM
+int launch_wprep(const WPrepDesc& d, cudaStream_t st);
+#endif
+
 // ---- small device helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

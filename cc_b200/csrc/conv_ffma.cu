@@ -411,6 +411,30 @@ static int pick_impl(const ccb_conv_desc* d, int op) {
     }
 }
 
+// rows of W floats -> rows of Wp >= W floats, zero tail
+__global__ void __launch_bounds__(256) pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int W,
+                                                       int Wp) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= rows * Wp) return;
+    const long long r = i / Wp;
+    const int x = (int)(i - r * Wp);
+    dst[i] = (x < W) ? __ldg(src + r * W + x) : 0.f;
+}
+
+// WGRAD on small feature maps whose width is not a multiple of 4 (26, 13, 7 ...): the tensor-core kernel reads
+// 16-byte pixel chunks, so x and dy are first copied into rows padded to a multiple of 4 with zeros - a zero dy
+// column contributes nothing and a zero x column is exactly what the convolution's own zero padding would read.
+static bool wgrad_pad_desc(const ccb_conv_desc* d, ccb_conv_desc& dp, long long& xpf, long long& dypf) {
+    if (d->impl == CCB_CONV_IMPL_FFMA || (d->Wo % 4) == 0) return false;
+    dp = *d;
+    dp.Wo = (d->Wo + 3) & ~3;
+    dp.Wi = (d->Wi + 3) & ~3;
+    xpf = (long long)d->B * d->Ci * d->Hi * dp.Wi;
+    dypf = (long long)d->B * d->Co * d->Ho * dp.Wo;
+    if (xpf + dypf > (8ll << 20)) return false;                    // small maps only (<= 32 MiB of copies)
+    return tc_profitable(&dp, CCB_CONV_WGRAD);
+}
+
 }  // namespace ccb
 
 using namespace ccb;
@@ -418,6 +442,14 @@ using namespace ccb;
 extern "C" long long ccb_conv_workspace_floats(const ccb_conv_desc* d, int op) {
     if (!d) return -1;
     const long long bias_need = (op == CCB_CONV_WGRAD) ? (long long)d->Co * (((long long)d->B * d->Ho * d->Wo + BG_CHUNK - 1) / BG_CHUNK) : 0;
+    if (op == CCB_CONV_WGRAD) {
+        ccb_conv_desc dp;
+        long long xpf, dypf;
+        if (wgrad_pad_desc(d, dp, xpf, dypf)) {
+            const long long t = xpf + dypf + tc_workspace_floats(&dp, op);
+            return t > bias_need ? t : bias_need;
+        }
+    }
     if (d->impl != CCB_CONV_IMPL_FFMA && tc_supported(d, op) && pick_impl(d, op) > 0) {
         long long t = tc_workspace_floats(d, op);
         if (op != CCB_CONV_WGRAD && tma_conv_supported(d, op)) {
@@ -514,6 +546,25 @@ extern "C" int ccb_conv2d_wgrad(const ccb_conv_desc* d, const float* x, const fl
             return rc;
         }
     }
+    {
+        ccb_conv_desc dp;
+        long long xpf, dypf;
+        if (wgrad_pad_desc(d, dp, xpf, dypf) && work && xpf + dypf + tc_workspace_floats(&dp, CCB_CONV_WGRAD) <= work_floats) {
+            float* xp = work;
+            float* dyp = work + xpf;
+            CCB_LAUNCH(pad_rows_kernel, dim3((unsigned)((xpf + 255) / 256)), dim3(256), 0, stream, x, xp, (long long)d->B * d->Ci * d->Hi,
+                       d->Wi, dp.Wi);
+            CCB_LAUNCH(pad_rows_kernel, dim3((unsigned)((dypf + 255) / 256)), dim3(256), 0, stream, dy, dyp, (long long)d->B * d->Co * d->Ho,
+                       d->Wo, dp.Wo);
+            rc = check_launch("conv2d_wgrad pad");
+            if (rc) return rc;
+            rc = tc_wgrad(&dp, xp, dyp, dw, work + xpf + dypf, work_floats - xpf - dypf, d->impl != CCB_CONV_IMPL_TC_TF32,
+                          (cudaStream_t)stream);
+            if (rc) return rc;
+            if (db) rc = launch_bias_grad(dy, db, d->B, d->Co, d->Ho * d->Wo, work, work_floats, (cudaStream_t)stream);
+            return rc;
+        }
+    }
     a.x = x; a.dy = dy; a.out = dw; a.work = work; a.act = CCB_ACT_NONE;
     a.M = a.Ci * a.kh * a.kw; a.N = a.Co; a.K = a.B * a.Ho * a.Wo;
     rc = launch_gemm<MODE_WGRAD>(a, (long long)a.M * a.N, work_floats, (cudaStream_t)stream, "conv2d_wgrad");
@@ -530,7 +581,12 @@ extern "C" int ccb_act_bwd(const float* dy, const float* y, float* dz, long long
     return check_launch("act_bwd");
 }
 
-extern "C" int ccb_bias_grad(const float* dy, float* db, int B, int C, int plane, ccb_stream_t stream) {
+extern "C" long long ccb_bias_grad_workspace_floats(int B, int C, int plane) {
+    const long long nsplit = ((long long)B * plane + BG_CHUNK - 1) / BG_CHUNK;
+    return nsplit > 1 ? (long long)C * nsplit : 0;
+}
+extern "C" int ccb_bias_grad(const float* dy, float* db, int B, int C, int plane, float* work, long long work_floats,
+                             ccb_stream_t stream) {
     CCB_REQUIRE(dy && db, CCB_ERR_ARG, "bias_grad: null pointer");
-    return launch_bias_grad(dy, db, B, C, plane, nullptr, 0, (cudaStream_t)stream);
+    return launch_bias_grad(dy, db, B, C, plane, work, work_floats, (cudaStream_t)stream);
 }

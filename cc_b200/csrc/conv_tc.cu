@@ -386,29 +386,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcArgs a) 
 
 // Weight re-layout: wp[n][t*cpad + c] = w[(co,ci) by mode][tap(t)], zero padded to Kp.
 //   mode 0 (fprop): n = co, c = ci : w[n][c][tap]        mode 1 (dgrad): n = ci, c = co : w[c][n][tap]
-struct PrepArgs {
-    const float* w;
-    float* wp;
-    int N, Cc, KK, ntaps, cpad, Kp, mode, Ci;
-    signed char tap_index[TC_MAX_TAPS];
-};
-
-__global__ void __launch_bounds__(256) wprep_kernel(const PrepArgs a) {
-    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= (long long)a.N * a.Kp) return;
-    int n = (int)(i / a.Kp), k = (int)(i - (long long)n * a.Kp);
-    int t = k / a.cpad, c = k - t * a.cpad;
-    float v = 0.f;
-    if (t < a.ntaps && c < a.Cc) {
-        int tap = a.tap_index[t];
-        v = (a.mode == 0) ? __ldg(a.w + ((long long)n * a.Cc + c) * a.KK + tap)
-                          : __ldg(a.w + ((long long)c * a.Ci + n) * a.KK + tap);
-    }
-    const float h = tf32_hi(v);
-    a.wp[i] = h;                                        // hi copy [N][Kp]
-    a.wp[(long long)a.N * a.Kp + i] = v - h;            // lo copy right behind it
-}
-
 static int roundup(int v, int m) { return (v + m - 1) / m * m; }
 
 void launch_splitk_reduce(const float* work, float* out, const float* bias, const float* res, long long numel, int splits,
@@ -436,11 +413,12 @@ static int launch_tc(TcArgs& a, const float* w, int mode, int N, int Cc, int KK,
     const long long wp_floats = 2ll * N * a.Kp;                  // tf32 hi copy + lo copy
     CCB_REQUIRE(wp_floats + (splits > 1 ? (long long)splits * a.out_numel : 0) <= work_floats, CCB_ERR_ARG,
                 "conv_tc: workspace too small (%lld floats)", work_floats);
-    PrepArgs p;
-    p.w = w; p.wp = work; p.N = N; p.Cc = Cc; p.KK = KK; p.ntaps = a.ntaps; p.cpad = a.cpad; p.Kp = a.Kp; p.mode = mode; p.Ci = Ci;
+    WPrepDesc p;
+    memset(&p, 0, sizeof(p));
+    p.w = w; p.wp = work; p.N = N; p.Cc = Cc; p.KK = KK; p.ntaps = a.ntaps; p.Kp = a.Kp; p.mode = mode; p.Ci = Ci;
+    p.layout = WPREP_TC; p.p0 = a.cpad;
     for (int t = 0; t < a.ntaps; ++t) p.tap_index[t] = tap_index[t];
-    CCB_LAUNCH(wprep_kernel, dim3((unsigned)(((long long)N * a.Kp + 255) / 256)), dim3(256), 0, st, p);
-    int rc = check_launch("conv_tc wprep");
+    int rc = launch_wprep(p, st);
     if (rc) return rc;
     a.wp = work;
     a.Ntot = N;

@@ -108,6 +108,38 @@ __device__ __forceinline__ void tm_umma_tf32(uint32_t tmem_d, uint64_t adesc, ui
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Warp-uniform issue: every lane runs the surrounding code (so descriptors stay in uniform registers and no
+// divergent region is entered), only the leader's predicate lets the instruction through.
+// Descriptors are passed as their two 32-bit halves: the high half is constant per operand kind.
+__device__ __forceinline__ void tm_umma_tf32_p(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tm_commit_p(uint64_t* bar, uint32_t leader) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(smem_addr(bar)), "r"(leader)
+        : "memory");
+}
+// halves of the shared-memory matrix descriptors (version 1): low = start >> 4 | LBO >> 4 << 16, high = SBO >> 4 | 1 << 14 | layout << 29
+constexpr uint32_t DESC_A_MN_LO = (4096u >> 4) << 16, DESC_A_MN_HI = (512u >> 4) | (1u << 14) | (1u << 29);   // MN-major SWIZZLE_128B_BASE32B
+constexpr uint32_t DESC_K_LO = (16u >> 4) << 16, DESC_K_HI = (1024u >> 4) | (1u << 14) | (2u << 29);          // K-major SWIZZLE_128B
+__device__ __forceinline__ void tm_prefetch_map(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
 __device__ __forceinline__ void tm_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
@@ -343,32 +375,6 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 }
 
-// weight preparation for the TMA path: wp[n][u*cb + j] = w[...][tap(slot(u))], split into tf32 hi / lo copies
-struct TmaPrepArgs {
-    const float* w;
-    float* wp;
-    int N, Cc, KK, Ci, mode, cb, cblocks, units, Kp;
-    signed char tap_index[TM_MAX_SLOTS];
-};
-__global__ void __launch_bounds__(256) tma_wprep_kernel(const TmaPrepArgs a) {
-    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= (long long)a.N * a.Kp) return;
-    const int n = (int)(i / a.Kp), k = (int)(i - (long long)n * a.Kp);
-    const int unit = k / a.cb, j = k - unit * a.cb;
-    float v = 0.f;
-    if (unit < a.units) {
-        const int slot = unit / a.cblocks, c = (unit - slot * a.cblocks) * a.cb + j;
-        const int tap = a.tap_index[slot];
-        if (c < a.Cc && tap >= 0)
-            v = (a.mode == 0) ? __ldg(a.w + ((long long)n * a.Cc + c) * a.KK + tap) : __ldg(a.w + ((long long)c * a.Ci + n) * a.KK + tap);
-    }
-    uint32_t hb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-    const float h = __uint_as_float(hb);
-    a.wp[i] = h;
-    a.wp[(long long)a.N * a.Kp + i] = v - h;
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -416,20 +422,19 @@ static int launch_tma(const float* x, int B, int Cc, int Hin, int Win, const flo
     a.out_numel = out_numel; a.partial = partial;
     a.bias = bias; a.res = res; a.out = out; a.act = act; a.slope = slope; a.soft = g_tma_soft;
     { const char* e = getenv("CCB_TMA_DBG"); a.dbg = e ? atoi(e) : 0; }
-    TmaPrepArgs p;
+    WPrepDesc p;
     memset(&p, 0, sizeof(p));
     CCB_REQUIRE(ntaps <= TM_MAX_SLOTS, CCB_ERR_ARG, "conv_tma: too many taps");
     for (int t = 0; t < TM_MAX_SLOTS; ++t) {
         a.off_y[t] = (signed char)(t < ntaps ? off_y[t] : 0);
         a.off_x[t] = (signed char)(t < ntaps ? off_x[t] : 0);
-        p.tap_index[t] = (signed char)(t < ntaps ? tap_index[t] : -1);
+        p.tap_index[t] = (signed char)(t < ntaps ? tap_index[t] : 0);
     }
     const long long wp_floats = 2ll * N * Kp;
     CCB_REQUIRE(wp_floats <= work_floats, CCB_ERR_ARG, "conv_tma: workspace too small");
-    p.w = w; p.wp = work; p.N = N; p.Cc = Cc; p.KK = KK; p.Ci = Ci; p.mode = mode; p.cb = a.cb; p.cblocks = a.cblocks;
-    p.units = a.units; p.Kp = Kp;
-    CCB_LAUNCH(tma_wprep_kernel, dim3((unsigned)(((long long)N * Kp + 255) / 256)), dim3(256), 0, st, p);
-    int rc = check_launch("conv_tma wprep");
+    p.w = w; p.wp = work; p.N = N; p.Cc = Cc; p.KK = KK; p.Ci = Ci; p.mode = mode; p.Kp = Kp; p.ntaps = ntaps;
+    p.layout = WPREP_TMA; p.p0 = a.cb; p.p1 = a.cblocks; p.p2 = a.units;
+    int rc = launch_wprep(p, st);
     if (rc) return rc;
     const int ntile_max = N < 128 ? N : 128;
     int nalloc = 16;
@@ -496,7 +501,7 @@ struct SlabArgs {
     float* out;
     int act;
     float slope;
-    int nstages, nbox, b_tile_bytes, soft;
+    int nstages, nbox, b_tile_bytes, soft, dbg;
     signed char off_y[TM_MAX_SLOTS], off_x[TM_MAX_SLOTS];
 };
 
@@ -517,6 +522,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     uint64_t* accum_bar = bars + 28;
     uint32_t* tmem_slot = (uint32_t*)(bars + 29);
     int* toff = (int*)(bars + 32);       // [64] slab offset of each tap
+    long long* trace = (long long*)(bars + 64);   // bring-up only (a.dbg & 32): [7][64] time stamps of CTA 0
+    const bool tracing = (a.dbg & 32) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    const long long t_start = clock64();
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int t = blockIdx.x;
@@ -539,7 +547,46 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         const int tp = tid - 64;
         toff[tp] = (tp < a.ntaps) ? (a.off_y[tp] - a.oy_lo) * a.SW + (a.off_x[tp] - a.ox_lo) : 0;
     }
+    // ---- producer state (thread 0): slabs and weight tiles are requested in k-stage order ----
+    const int last_block = (ktiles > 0) ? min((kt_beg + ktiles - 1) / a.kt_full, a.cblocks - 1) : first_block - 1;
+    const int nblocks = last_block - first_block + 1;             // slabs this CTA goes through
+    int p_it = 0, p_s = 0, p_ph = 0;                               // next k-stage to request, its ring slot and phase
+    int p_slab = 0, p_sb = 0, p_sph = 0;                           // next slab to request, its buffer and phase
+    int p_blk = 0, p_left = 0;                                     // block of stage p_it, its remaining stages
+    const uint32_t b_tx = (uint32_t)((THREE ? 2 : 1) * a.nbox * 128);
+    auto produce = [&](int limit, bool nowait) {                   // request k-stages p_it .. limit-1 (nowait: stop at the first wait)
+        for (; p_it < limit; ++p_it) {
+            if (p_left == 0) {                                     // first stage of a block
+                if (p_it > 0) ++p_blk;
+                const int cb = first_block + p_blk;
+                const int full = (cb < a.cblocks - 1) ? a.kt_full : a.ktiles - (a.cblocks - 1) * a.kt_full;
+                p_left = (p_it == 0) ? full - (kt_beg - cb * a.kt_full) : full;
+            }
+            // the slab of this block and (double buffered) of the next one
+            const int want = min(nblocks, p_blk + a.nslab);
+            while (p_slab < want) {
+                if (p_slab >= a.nslab) {
+                    if (nowait) return;
+                    tm_mbar_wait(&slab_empty[p_sb], p_sph ^ 1, a.soft, 6, p_it);
+                }
+                tm_mbar_expect_tx(&slab_full[p_sb], (uint32_t)a.slab_tx);
+                tma_load_4d(slab0 + p_sb * a.slab_bytes, &map_x, &slab_full[p_sb], xs, ys, (first_block + p_slab) * a.cs, b);
+                ++p_slab;
+                if (++p_sb == a.nslab) { p_sb = 0; p_sph ^= 1; }
+            }
+            if (p_it >= NST) tm_mbar_wait(&empty_bar[p_s], p_ph ^ 1, a.soft, 1, p_it);
+            unsigned char* bt = smem + p_s * stage_bytes + (THREE ? 2 : 1) * TM_A_BYTES;
+            tm_mbar_expect_tx(&b_full[p_s], b_tx);
+            tma_load_2d(bt, &map_b, &b_full[p_s], (kt_beg + p_it) * 32, n0);
+            if (THREE) tma_load_2d(bt + a.nbox * 128, &map_b, &b_full[p_s], (kt_beg + p_it) * 32, a.Ntot + n0);
+            if (tracing && p_it < 64) trace[0 * 64 + p_it] = clock64() - t_start;
+            --p_left;
+            if (++p_s == NST) { p_s = 0; p_ph ^= 1; }
+        }
+    };
     if (tid == 0) {
+        tm_prefetch_map(&map_x);
+        tm_prefetch_map(&map_b);
         for (int s = 0; s < NST; ++s) {
             tm_mbar_init(&a_full[s], 8);
             tm_mbar_init(&b_full[s], 1);
@@ -551,6 +598,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         tm_mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        produce(min(ktiles, NST), true);                           // the first ring of loads needs no consumer: start it before the CTA sync
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(512u) : "memory");
@@ -560,61 +608,40 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (tracing && tid == 0) trace[7 * 64] = clock64() - t_start;
 
     if (warp == 0) {
-        // ===================== TMA producer (one thread): slabs + weight tiles =====================
-        if (lane == 0) {
-            int issued = 0;                                        // slabs requested so far
-            const int last_block = (ktiles > 0) ? min((kt_beg + ktiles - 1) / a.kt_full, a.cblocks - 1) : first_block - 1;
-            for (int it = 0; it < ktiles; ++it) {
-                const int kt = kt_beg + it;
-                const int cblock = min(kt / a.kt_full, a.cblocks - 1);
-                // the slab of this block, and (double buffered) the next one as soon as this block starts
-                const int want = min(last_block, cblock + (a.nslab - 1)) - first_block + 1;
-                while (issued < want) {
-                    const int sb = issued % a.nslab;
-                    if (issued >= a.nslab) tm_mbar_wait(&slab_empty[sb], ((issued / a.nslab) - 1) & 1, a.soft, 6, it);
-                    tm_mbar_expect_tx(&slab_full[sb], (uint32_t)a.slab_tx);
-                    tma_load_4d(slab0 + sb * a.slab_bytes, &map_x, &slab_full[sb], xs, ys, (first_block + issued) * a.cs, b);
-                    ++issued;
-                }
-                const int s = it % NST;
-                if (it >= NST) tm_mbar_wait(&empty_bar[s], ((it / NST) - 1) & 1, a.soft, 1, it);
-                unsigned char* bt = smem + s * stage_bytes + (THREE ? 2 : 1) * TM_A_BYTES;
-                tm_mbar_expect_tx(&b_full[s], (uint32_t)((THREE ? 2 : 1) * a.nbox * 128));
-                tma_load_2d(bt, &map_b, &b_full[s], kt * 32, n0);
-                if (THREE) tma_load_2d(bt + a.nbox * 128, &map_b, &b_full[s], kt * 32, a.Ntot + n0);
-            }
-        }
+        // ===================== TMA producer (one thread): the rest of the slabs + weight tiles =====================
+        if (lane == 0) produce(ktiles, false);
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
+        // ===================== MMA issuer: the whole warp runs the loop, lane 0's predicate issues =====================
         const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(TM_M >> 4) << 24);
         const uint32_t idesc_n1 = idesc_base | ((uint32_t)(a.nbox >> 3) << 17);
         const uint32_t idesc_n2 = idesc_base | ((uint32_t)((2 * a.nbox) >> 3) << 17);
+        const uint32_t leader = (lane == 0) ? 1u : 0u;
+        const uint32_t smem16 = smem_addr(smem) >> 4, stage16 = (uint32_t)stage_bytes >> 4;
+        int s = 0;
+        uint32_t ph = 0;
         for (int it = 0; it < ktiles; ++it) {
-            const int s = it % NST;
-            tm_mbar_wait(&b_full[s], (it / NST) & 1, a.soft, 2, it);
-            tm_mbar_wait(&a_full[s], (it / NST) & 1, a.soft, 3, it);
+            tm_mbar_wait(&b_full[s], ph, a.soft, 2, it);
+            tm_mbar_wait(&a_full[s], ph, a.soft, 3, it);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t st = smem_addr(smem + s * stage_bytes);
-                const uint32_t a_hi = st, a_lo = st + TM_A_BYTES;
-                const uint32_t bt = st + (THREE ? 2 : 1) * TM_A_BYTES;
+            if (tracing && lane == 0 && it < 64) trace[1 * 64 + it] = clock64() - t_start;
+            const uint32_t a_hi16 = smem16 + (uint32_t)s * stage16, a_lo16 = a_hi16 + (TM_A_BYTES >> 4);
+            const uint32_t b16 = a_hi16 + (((THREE ? 2 : 1) * TM_A_BYTES) >> 4);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t ah = tm_desc(a_hi + ks * 1024, 4096, 512, 1);
-                    const uint64_t bh = tm_desc(bt + ks * 32, 16, 1024, 2);
-                    const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
-                    tm_umma_tf32(tmem_base, ah, bh, THREE ? idesc_n2 : idesc_n1, acc);
-                    if (THREE) {
-                        const uint64_t al = tm_desc(a_lo + ks * 1024, 4096, 512, 1);
-                        tm_umma_tf32(tmem_base + 256u, al, bh, idesc_n1, acc);
-                    }
-                }
-                tm_commit(&empty_bar[s]);
-                if (it == ktiles - 1) tm_commit(accum_bar);
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+                tm_umma_tf32_p(tmem_base, (a_hi16 + ks * 64) | DESC_A_MN_LO, DESC_A_MN_HI, (b16 + ks * 2) | DESC_K_LO, DESC_K_HI,
+                               THREE ? idesc_n2 : idesc_n1, acc, leader);
+                if (THREE)
+                    tm_umma_tf32_p(tmem_base + 256u, (a_lo16 + ks * 64) | DESC_A_MN_LO, DESC_A_MN_HI, (b16 + ks * 2) | DESC_K_LO, DESC_K_HI,
+                                   idesc_n1, acc, leader);
             }
-            __syncwarp();
+            tm_commit_p(&empty_bar[s], leader);
+            if (it == ktiles - 1) tm_commit_p(accum_bar, leader);
+            if (tracing && lane == 0 && it < 64) trace[2 * 64 + it] = clock64() - t_start;
+            if (++s == NST) { s = 0; ph ^= 1; }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
@@ -632,24 +659,25 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const int k = w8 * 4 + i;
             dst[i] = (uint32_t)(mb * 4096 + k * 128 + (((pxg >> 1) ^ (k & 3)) << 5) + (pxg & 1) * 16);
         }
-        int cblock = first_block, q = 0;
+        int cblock = first_block;
         int kl_stage = kt_beg - cblock * a.kt_full;                             // k-stage inside the block
         int blk_stages = (cblock < a.cblocks - 1) ? a.kt_full : a.ktiles - (a.cblocks - 1) * a.kt_full;
         int nch = min(a.cs, a.Cin - cblock * a.cs);
         int q32 = 32 / nch, r32 = 32 - q32 * nch;
         int tap0 = (kl_stage * 32 + w8 * 4) / nch, c0 = (kl_stage * 32 + w8 * 4) - tap0 * nch;
         bool need_slab = true;                                                  // this warp has not looked at the current slab yet
+        int sb = 0, s = 0;                                                      // slab buffer / ring slot of stage `it` ...
+        uint32_t sph = 0, ph = 0;                                               // ... and their phases
         for (int it = 0; it < ktiles; ++it) {
-            const int sb = q % a.nslab;
             if ((it & 1) == grp) {
                 const float* slab = (const float*)(slab0 + sb * a.slab_bytes);
                 if (need_slab) {
-                    tm_mbar_wait(&slab_full[sb], (q / a.nslab) & 1, a.soft, 4, it);
+                    tm_mbar_wait(&slab_full[sb], sph, a.soft, 4, it);
                     need_slab = false;
                 }
-                const int s = it % NST;
-                if (it >= NST) tm_mbar_wait(&empty_bar[s], ((it / NST) - 1) & 1, a.soft, 7, it);
+                if (it >= NST) tm_mbar_wait(&empty_bar[s], ph ^ 1, a.soft, 7, it);
                 unsigned char* st = smem + s * stage_bytes;
+                if (tracing && w8 == 0 && lane == 0 && it < 64) trace[3 * 64 + it] = clock64() - t_start;
                 int sidx[4];
                 bool kval[4];
                 {
@@ -689,15 +717,19 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     *(float4*)(st + dst[i]) = v[i];
                     if (THREE) *(float4*)(st + TM_A_BYTES + dst[i]) = tf32_rest4(v[i]);
                 }
+                if (tracing && w8 == 0 && lane == 0 && it < 64) trace[4 * 64 + it] = clock64() - t_start;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) tm_mbar_arrive(&a_full[s]);
+                if (tracing && w8 == 0 && lane == 0 && it < 64) trace[5 * 64 + it] = clock64() - t_start;
             }
             ++kl_stage;
             const bool block_done = (kl_stage == blk_stages);
             if ((block_done || it == ktiles - 1) && lane == 0) tm_mbar_arrive(&slab_empty[sb]);
+            if (++s == NST) { s = 0; ph ^= 1; }
             if (block_done && it + 1 < ktiles) {
-                ++cblock; ++q; kl_stage = 0; need_slab = true;
+                ++cblock; kl_stage = 0; need_slab = true;
+                if (++sb == a.nslab) { sb = 0; sph ^= 1; }
                 blk_stages = (cblock < a.cblocks - 1) ? a.kt_full : a.ktiles - (a.cblocks - 1) * a.kt_full;
                 nch = min(a.cs, a.Cin - cblock * a.cs);
                 q32 = 32 / nch; r32 = 32 - q32 * nch;
@@ -708,6 +740,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             }
         }
         if (ktiles > 0) tm_mbar_wait(accum_bar, 0, a.soft, 5, 0);
+        if (tracing && warp == 2 && lane == 0) trace[6 * 64 + 0] = clock64() - t_start;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q4 = warp & 3, colq = (warp - 2) >> 2;        // 4 warps per TMEM lane quarter split the columns
         const int oy = y0 + q4, ox = x0 + lane;
@@ -754,38 +787,16 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
+    if (tracing && tid == 0) {
+        printf("slab trace: prologue_done %lld epilogue_start %lld end %lld (cycles)\n", trace[7 * 64], trace[6 * 64], (long long)(clock64() - t_start));
+        for (int it = 0; it < ktiles && it < 64; ++it)
+            printf("it %2d  tma %6lld  mma_ready %6lld  mma_issued %6lld  cut_start %6lld  cut_stored %6lld  cut_arrived %6lld\n", it,
+                   trace[0 * 64 + it], trace[1 * 64 + it], trace[2 * 64 + it], trace[3 * 64 + it], trace[4 * 64 + it], trace[5 * 64 + it]);
+    }
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
-}
-
-// weights for the slab kernel: wp[n][kt*32 + j], k-stage kt -> (block, flattened (tap, channel) index), tf32 hi / lo copies
-struct SlabPrepArgs {
-    const float* w;
-    float* wp;
-    int N, Cc, KK, Ci, mode, cs, cblocks, kt_full, Kp, ntaps;
-    signed char tap_index[TM_MAX_SLOTS];
-};
-__global__ void __launch_bounds__(256) slab_wprep_kernel(const SlabPrepArgs a) {
-    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= (long long)a.N * a.Kp) return;
-    const int n = (int)(i / a.Kp), k = (int)(i - (long long)n * a.Kp);
-    const int kt = k >> 5;
-    const int cblock = min(kt / a.kt_full, a.cblocks - 1);
-    const int kl = (kt - cblock * a.kt_full) * 32 + (k & 31);
-    const int nch = min(a.cs, a.Cc - cblock * a.cs);
-    const int slot = kl / nch, c = cblock * a.cs + (kl - slot * nch);
-    float v = 0.f;
-    if (slot < a.ntaps) {
-        const int tap = a.tap_index[slot];
-        v = (a.mode == 0) ? __ldg(a.w + ((long long)n * a.Cc + c) * a.KK + tap) : __ldg(a.w + ((long long)c * a.Ci + n) * a.KK + tap);
-    }
-    uint32_t hb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-    const float h = __uint_as_float(hb);
-    a.wp[i] = h;
-    a.wp[(long long)a.N * a.Kp + i] = v - h;
 }
 
 struct SlabPlan {
@@ -815,7 +826,7 @@ static SlabPlan slab_plan(const int* off_y, const int* off_x, int ntaps, int in_
     int g = nt, r = 32;                    // channel granularity that makes cs * ntaps a multiple of 32
     while (r) { int q = g % r; g = r; r = q; }
     const int align = 32 / g;
-    const int total = 224 * 1024;
+    const int total = 220 * 1024;
     for (int nst = 3; nst >= 2 && !p.ok; --nst) {
         const int budget = total - nst * stage;
         for (int cb = 1; cb <= Cc && !p.ok; ++cb) {
@@ -836,7 +847,7 @@ static SlabPlan slab_plan(const int* off_y, const int* off_x, int ntaps, int in_
     p.kt_full = cdiv(p.cs * nt, 32);
     const int tail = Cc - (p.cblocks - 1) * p.cs;
     p.ktiles = (p.cblocks - 1) * p.kt_full + cdiv(tail * nt, 32);
-    p.smem = p.nstages * stage + p.nslab * p.slab_bytes + 1024 + 1024;
+    p.smem = p.nstages * stage + p.nslab * p.slab_bytes + 1024 + 1024 + 4096;   // + barriers / tap table / bring-up trace
     return p;
 }
 
@@ -861,7 +872,8 @@ static int launch_slab(const float* x, int B, int Cc, int Hin, int Win, const fl
     a.out_numel = out_numel; a.partial = partial;
     a.bias = bias; a.res = res; a.out = out; a.act = act; a.slope = slope; a.soft = g_tma_soft;
     a.nstages = p.nstages; a.nbox = p.nbox; a.b_tile_bytes = p.b_tile_bytes;
-    SlabPrepArgs pa;
+    { const char* e = getenv("CCB_TMA_DBG"); a.dbg = e ? atoi(e) : 0; }
+    WPrepDesc pa;
     memset(&pa, 0, sizeof(pa));
     for (int t = 0; t < TM_MAX_SLOTS; ++t) {
         a.off_y[t] = (signed char)(t < ntaps ? off_y[t] : 0);
@@ -870,10 +882,9 @@ static int launch_slab(const float* x, int B, int Cc, int Hin, int Win, const fl
     }
     const int Kp = a.ktiles * 32;
     CCB_REQUIRE(2ll * N * Kp <= wp_floats, CCB_ERR_ARG, "conv_slab: workspace too small");
-    pa.w = w; pa.wp = work; pa.N = N; pa.Cc = Cc; pa.KK = KK; pa.Ci = Ci; pa.mode = mode; pa.cs = p.cs; pa.cblocks = p.cblocks;
-    pa.kt_full = p.kt_full; pa.Kp = Kp; pa.ntaps = ntaps;
-    CCB_LAUNCH(slab_wprep_kernel, dim3((unsigned)(((long long)N * Kp + 255) / 256)), dim3(256), 0, st, pa);
-    int rc = check_launch("conv_slab wprep");
+    pa.w = w; pa.wp = work; pa.N = N; pa.Cc = Cc; pa.KK = KK; pa.Ci = Ci; pa.mode = mode; pa.Kp = Kp; pa.ntaps = ntaps;
+    pa.layout = WPREP_SLAB; pa.p0 = p.cs; pa.p1 = p.cblocks; pa.p2 = p.kt_full;
+    int rc = launch_wprep(pa, st);
     if (rc) return rc;
     alignas(64) CUtensorMap map_x, map_b;
     {
@@ -1094,6 +1105,8 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     const int ky_lo = tap0 / a.kw;
 
     if (tid == 0) {
+        tm_prefetch_map(&map_x);
+        tm_prefetch_map(&map_dy);
         for (int s = 0; s < NST; ++s) {
             tm_mbar_init(&tma_full[s], 1);
             tm_mbar_init(&a_full[s], 8);
@@ -1125,43 +1138,44 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             int b = g / per_img;
             int r = g - b * per_img;
             int oy = r / a.segs, seg = r - oy * a.segs;
+            int s = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < nst; ++it) {
-                const int s = it % NST;
-                if (it >= NST) tm_mbar_wait(&empty_bar[s], ((it / NST) - 1) & 1, a.soft, 1, it);
+                if (it >= NST) tm_mbar_wait(&empty_bar[s], ph ^ 1, a.soft, 1, it);
                 unsigned char* st = smem + s * stage_bytes;
                 tm_mbar_expect_tx(&tma_full[s], tx_bytes);
                 tma_load_4d(st + ab_bytes, &map_x, &tma_full[s], seg * 32 * a.stride - a.pad - a.dx0, oy * a.stride + ky_lo - a.pad, c0, b);
                 tma_load_4d(st + (THREE ? 2 : 1) * TM_A_BYTES, &map_dy, &tma_full[s], seg * 32, oy, n0, b);
                 if (++seg == a.segs) { seg = 0; if (++oy == a.Ho) { oy = 0; ++b; } }
+                if (++s == NST) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
+        // the whole warp runs the loop, lane 0's predicate issues (both operands K-major SWIZZLE_128B)
         const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TM_M >> 4) << 24);
         const uint32_t idesc_n1 = idesc_base | ((uint32_t)(a.nbox >> 3) << 17);
         const uint32_t idesc_n2 = idesc_base | ((uint32_t)((2 * a.nbox) >> 3) << 17);
+        const uint32_t leader = (lane == 0) ? 1u : 0u;
+        const uint32_t smem16 = smem_addr(smem) >> 4, stage16 = (uint32_t)stage_bytes >> 4;
+        int s = 0;
+        uint32_t ph = 0;
         for (int it = 0; it < nst; ++it) {
-            const int s = it % NST;
-            tm_mbar_wait(&a_full[s], (it / NST) & 1, a.soft, 3, it);
+            tm_mbar_wait(&a_full[s], ph, a.soft, 3, it);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t st = smem_addr(smem + s * stage_bytes);
-                const uint32_t a_hi = st, a_lo = st + TM_A_BYTES;
-                const uint32_t bt = st + (THREE ? 2 : 1) * TM_A_BYTES;
+            const uint32_t a_hi16 = smem16 + (uint32_t)s * stage16, a_lo16 = a_hi16 + (TM_A_BYTES >> 4);
+            const uint32_t b16 = a_hi16 + (((THREE ? 2 : 1) * TM_A_BYTES) >> 4);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t ah = tm_desc(a_hi + ks * 32, 16, 1024, 2);
-                    const uint64_t bh = tm_desc(bt + ks * 32, 16, 1024, 2);
-                    const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
-                    tm_umma_tf32(tmem_base, ah, bh, THREE ? idesc_n2 : idesc_n1, acc);
-                    if (THREE) {
-                        const uint64_t al = tm_desc(a_lo + ks * 32, 16, 1024, 2);
-                        tm_umma_tf32(tmem_base + 256u, al, bh, idesc_n1, acc);
-                    }
-                }
-                tm_commit(&empty_bar[s]);
-                if (it == nst - 1) tm_commit(accum_bar);
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+                tm_umma_tf32_p(tmem_base, (a_hi16 + ks * 2) | DESC_K_LO, DESC_K_HI, (b16 + ks * 2) | DESC_K_LO, DESC_K_HI,
+                               THREE ? idesc_n2 : idesc_n1, acc, leader);
+                if (THREE)
+                    tm_umma_tf32_p(tmem_base + 256u, (a_lo16 + ks * 2) | DESC_K_LO, DESC_K_HI, (b16 + ks * 2) | DESC_K_LO, DESC_K_HI,
+                                   idesc_n1, acc, leader);
             }
-            __syncwarp();
+            tm_commit_p(&empty_bar[s], leader);
+            if (it == nst - 1) tm_commit_p(accum_bar, leader);
+            if (++s == NST) { s = 0; ph ^= 1; }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
@@ -1183,9 +1197,10 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             rdst[j] = (uint32_t)(r * 128 + ((pxg ^ (r & 7)) << 4));
         }
         const int b4 = a.nbox * 8;                                             // float4 of the dy tile
+        int s = grp % NST;
+        uint32_t ph = (grp / NST) & 1;
         for (int it = grp; it < nst; it += 2) {
-            const int s = it % NST;
-            tm_mbar_wait(&tma_full[s], (it / NST) & 1, a.soft, 4, it);
+            tm_mbar_wait(&tma_full[s], ph, a.soft, 4, it);
             unsigned char* st = smem + s * stage_bytes;
             const float* slab = (const float*)(st + ab_bytes);
             float4 v[4];
@@ -1225,6 +1240,8 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) tm_mbar_arrive(&a_full[s]);
+            s += 2;
+            if (s >= NST) { s -= NST; ph ^= 1; }
         }
         if (nst > 0) tm_mbar_wait(accum_bar, 0, a.soft, 5, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

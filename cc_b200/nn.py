@@ -149,7 +149,9 @@ class _ConvT2dFn(torch.autograd.Function):
             dw = None if direct else dw
         if has_bias and ctx.needs_input_grad[2]:
             db, direct = _grad_slot(ctx.params[1], w.new_empty(Cout))
-            _lib.check(_lib.lib().ccb_bias_grad(_lib.ptr(dz), _lib.ptr(db), B, Cout, H * W, _lib.stream(dz)), 'bias_grad')
+            work, wf = _workspace(dz.device, _lib.lib().ccb_bias_grad_workspace_floats(B, Cout, H * W))
+            _lib.check(_lib.lib().ccb_bias_grad(_lib.ptr(dz), _lib.ptr(db), B, Cout, H * W, _lib.ptr(work), wf, _lib.stream(dz)),
+                       'bias_grad')
             db = None if direct else db
         return dx, dw, db, None, None, None, None, None
 

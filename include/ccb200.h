@@ -224,7 +224,11 @@ int ccb_conv2d_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, fl
 /* dz = dy * act'(.) expressed through the activation OUTPUT y (in place allowed: dz == dy). */
 int ccb_act_bwd(const float* dy, const float* y, float* dz, long long numel, int act, float slope,
                 ccb_stream_t stream);
-int ccb_bias_grad(const float* dy, float* db, int B, int C, int plane, ccb_stream_t stream);
+/* db[c] = sum over (b, pixel) of dy; `work` (ccb_bias_grad_workspace_floats) lets large planes be reduced in two
+ * deterministic stages, without it one block per channel does the whole sum */
+long long ccb_bias_grad_workspace_floats(int B, int C, int plane);
+int ccb_bias_grad(const float* dy, float* db, int B, int C, int plane, float* work, long long work_floats,
+                  ccb_stream_t stream);
 /* bring-up aid (layout probe): bit 0 swaps the LBO/SBO strides of the UMMA shared-memory descriptors
  * (must produce wrong results), bit 2 selects the K-major no-swizzle operand layout instead of the
  * default SWIZZLE_128B one (must produce identical results), bit 3 turns the TMA-fed kernels off so that

@@ -21,6 +21,9 @@ CASES = [  # B, Ci, H, W, Co, k, s, p, op
     (2, 3, 20, 64, 32, 7, 2, 3, 'fprop'),        # stride 2, 3 channels, 7x7 (disp conv1)
     (2, 32, 16, 64, 64, 3, 2, 1, 'fprop'),       # stride 2
     (2, 160, 8, 32, 48, 3, 1, 1, 'fprop'),       # several channel blocks (double-buffered slabs)
+    (2, 32, 16, 64, 256, 3, 2, 1, 'dgrad'),      # 1-tap parity class with many short channel blocks
+    (2, 64, 32, 64, 128, 3, 2, 1, 'dgrad'),
+    (2, 32, 16, 64, 64, 1, 2, 0, 'fprop'),       # 1x1 stride 2
     (4, 128, 32, 104, 128, 3, 1, 1, 'fprop'),    # real layers from here on
     (4, 32, 128, 416, 32, 7, 1, 3, 'fprop'),
     (4, 16, 256, 832, 16, 3, 1, 1, 'fprop'),
@@ -111,7 +114,8 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'case':
         run_case(int(sys.argv[2]))
     else:
-        for i in range(len(CASES)):
+        sel = [int(v) for v in os.environ.get('CCB_PROBE_CASES', '').split(',') if v] or range(len(CASES))
+        for i in sel:
             try:
                 r = subprocess.run([sys.executable, __file__, 'case', str(i)], capture_output=True, text=True, timeout=120)
                 line = [l for l in r.stdout.splitlines() if l.startswith('{')]

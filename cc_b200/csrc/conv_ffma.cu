@@ -397,7 +397,14 @@ long long tma_wgrad_workspace_floats(const ccb_conv_desc* d);
 int tma_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw, float* work, long long work_floats, int three,
               cudaStream_t st);
 static bool use_tma(const ccb_conv_desc* d, int op, const void* src) {
-    return (((uintptr_t)src) & 15) == 0 && tma_conv_supported(d, op) && tma_workspace_floats(d, op) >= 0;
+    if ((((uintptr_t)src) & 15) != 0 || !tma_conv_supported(d, op) || tma_workspace_floats(d, op) < 0) return false;
+    // measured on B200 (tools/tma_probe.py): the slab kernel wins every DGRAD and the FPROPs with a long K loop or
+    // >= 64 output channels; short thin FPROPs (K <= 512, N <= 32) and stride-2 FPROPs stay on the register-gather kernel
+    if (op == CCB_CONV_FPROP && d->kh > 1) {
+        if (d->stride != 1) return false;
+        if (d->Co < 64 && (long long)d->Ci * d->kh * d->kw < 512) return false;
+    }
+    return true;
 }
 
 // 0: FFMA, 1: tcgen05 3xTF32, 2: tcgen05 single TF32

@@ -501,7 +501,7 @@ struct SlabArgs {
     float* out;
     int act;
     float slope;
-    int nstages, nbox, b_tile_bytes, soft, dbg;
+    int nstages, nbox, b_tile_bytes, soft, dbg, mt;
     signed char off_y[TM_MAX_SLOTS], off_x[TM_MAX_SLOTS];
 };
 
@@ -532,7 +532,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int b = t / per_b;
     t -= b * per_b;
     const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
-    const int x0 = tx * 32, y0 = ty * 4;
+    const int x0 = tx * 32, y0 = ty * 4 * a.mt;                   // a CTA owns mt vertically stacked 4 x 32 tiles (one slab)
     const int n0 = blockIdx.y * 128;
     const int ntile = min(128, a.Ntot - n0);
     const int kt_beg = blockIdx.z * a.kt_per_split;
@@ -554,8 +554,11 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     int p_slab = 0, p_sb = 0, p_sph = 0;                           // next slab to request, its buffer and phase
     int p_blk = 0, p_left = 0;                                     // block of stage p_it, its remaining stages
     const uint32_t b_tx = (uint32_t)((THREE ? 2 : 1) * a.nbox * 128);
-    auto produce = [&](int limit, bool nowait) {                   // request k-stages p_it .. limit-1 (nowait: stop at the first wait)
+    int p_k = 0;                                                   // k-stage of p_it inside its tile
+    const int total_stages = a.mt * ktiles;
+    auto produce = [&](int limit, bool nowait) {                   // request stages p_it .. limit-1 (nowait: stop at the first wait)
         for (; p_it < limit; ++p_it) {
+            if (p_left == 0 && a.mt > 1) p_left = total_stages;   // stacked tiles share the one slab
             if (p_left == 0) {                                     // first stage of a block
                 if (p_it > 0) ++p_blk;
                 const int cb = first_block + p_blk;
@@ -577,8 +580,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             if (p_it >= NST) tm_mbar_wait(&empty_bar[p_s], p_ph ^ 1, a.soft, 1, p_it);
             unsigned char* bt = smem + p_s * stage_bytes + (THREE ? 2 : 1) * TM_A_BYTES;
             tm_mbar_expect_tx(&b_full[p_s], b_tx);
-            tma_load_2d(bt, &map_b, &b_full[p_s], (kt_beg + p_it) * 32, n0);
-            if (THREE) tma_load_2d(bt + a.nbox * 128, &map_b, &b_full[p_s], (kt_beg + p_it) * 32, a.Ntot + n0);
+            tma_load_2d(bt, &map_b, &b_full[p_s], (kt_beg + p_k) * 32, n0);
+            if (THREE) tma_load_2d(bt + a.nbox * 128, &map_b, &b_full[p_s], (kt_beg + p_k) * 32, a.Ntot + n0);
+            if (++p_k == ktiles) p_k = 0;
             if (tracing && p_it < 64) trace[0 * 64 + p_it] = clock64() - t_start;
             --p_left;
             if (++p_s == NST) { p_s = 0; p_ph ^= 1; }
@@ -598,7 +602,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         tm_mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        produce(min(ktiles, NST), true);                           // the first ring of loads needs no consumer: start it before the CTA sync
+        produce(min(total_stages, NST), true);                           // the first ring of loads needs no consumer: start it before the CTA sync
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(512u) : "memory");
@@ -612,7 +616,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer (one thread): the rest of the slabs + weight tiles =====================
-        if (lane == 0) produce(ktiles, false);
+        if (lane == 0) produce(total_stages, false);
     } else if (warp == 1) {
         // ===================== MMA issuer: the whole warp runs the loop, lane 0's predicate issues =====================
         const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(TM_M >> 4) << 24);
@@ -622,6 +626,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         const uint32_t smem16 = smem_addr(smem) >> 4, stage16 = (uint32_t)stage_bytes >> 4;
         int s = 0;
         uint32_t ph = 0;
+        for (int m = 0; m < a.mt; ++m) {
+        const uint32_t d0 = tmem_base + (uint32_t)(m * (THREE ? 3 : 1) * a.nbox), d1 = d0 + (uint32_t)(2 * a.nbox);
         for (int it = 0; it < ktiles; ++it) {
             tm_mbar_wait(&b_full[s], ph, a.soft, 2, it);
             tm_mbar_wait(&a_full[s], ph, a.soft, 3, it);
@@ -632,16 +638,17 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
-                tm_umma_tf32_p(tmem_base, (a_hi16 + ks * 64) | DESC_A_MN_LO, DESC_A_MN_HI, (b16 + ks * 2) | DESC_K_LO, DESC_K_HI,
+                tm_umma_tf32_p(d0, (a_hi16 + ks * 64) | DESC_A_MN_LO, DESC_A_MN_HI, (b16 + ks * 2) | DESC_K_LO, DESC_K_HI,
                                THREE ? idesc_n2 : idesc_n1, acc, leader);
                 if (THREE)
-                    tm_umma_tf32_p(tmem_base + 256u, (a_lo16 + ks * 64) | DESC_A_MN_LO, DESC_A_MN_HI, (b16 + ks * 2) | DESC_K_LO, DESC_K_HI,
+                    tm_umma_tf32_p(d1, (a_lo16 + ks * 64) | DESC_A_MN_LO, DESC_A_MN_HI, (b16 + ks * 2) | DESC_K_LO, DESC_K_HI,
                                    idesc_n1, acc, leader);
             }
             tm_commit_p(&empty_bar[s], leader);
-            if (it == ktiles - 1) tm_commit_p(accum_bar, leader);
+            if (it == ktiles - 1 && m == a.mt - 1) tm_commit_p(accum_bar, leader);
             if (tracing && lane == 0 && it < 64) trace[2 * 64 + it] = clock64() - t_start;
             if (++s == NST) { s = 0; ph ^= 1; }
+        }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
@@ -659,23 +666,26 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const int k = w8 * 4 + i;
             dst[i] = (uint32_t)(mb * 4096 + k * 128 + (((pxg >> 1) ^ (k & 3)) << 5) + (pxg & 1) * 16);
         }
+        int g = 0;                                                              // stages gone by (all tiles of this CTA)
+        bool need_slab = true;                                                  // this warp has not looked at the current slab yet
+        int sb = 0, s = 0;                                                      // slab buffer / ring slot of the stage ...
+        uint32_t sph = 0, ph = 0;                                               // ... and their phases
+        for (int m = 0; m < a.mt; ++m) {
+        const int thr_m = thr_off + m * 4 * s_in * a.SW;
         int cblock = first_block;
         int kl_stage = kt_beg - cblock * a.kt_full;                             // k-stage inside the block
         int blk_stages = (cblock < a.cblocks - 1) ? a.kt_full : a.ktiles - (a.cblocks - 1) * a.kt_full;
         int nch = min(a.cs, a.Cin - cblock * a.cs);
         int q32 = 32 / nch, r32 = 32 - q32 * nch;
         int tap0 = (kl_stage * 32 + w8 * 4) / nch, c0 = (kl_stage * 32 + w8 * 4) - tap0 * nch;
-        bool need_slab = true;                                                  // this warp has not looked at the current slab yet
-        int sb = 0, s = 0;                                                      // slab buffer / ring slot of stage `it` ...
-        uint32_t sph = 0, ph = 0;                                               // ... and their phases
-        for (int it = 0; it < ktiles; ++it) {
-            if ((it & 1) == grp) {
+        for (int it = 0; it < ktiles; ++it, ++g) {
+            if ((g & 1) == grp) {
                 const float* slab = (const float*)(slab0 + sb * a.slab_bytes);
                 if (need_slab) {
                     tm_mbar_wait(&slab_full[sb], sph, a.soft, 4, it);
                     need_slab = false;
                 }
-                if (it >= NST) tm_mbar_wait(&empty_bar[s], ph ^ 1, a.soft, 7, it);
+                if (g >= NST) tm_mbar_wait(&empty_bar[s], ph ^ 1, a.soft, 7, it);
                 unsigned char* st = smem + s * stage_bytes;
                 if (tracing && w8 == 0 && lane == 0 && it < 64) trace[3 * 64 + it] = clock64() - t_start;
                 int sidx[4];
@@ -685,7 +695,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         kval[i] = tap < a.ntaps;
-                        sidx[i] = thr_off + (kval[i] ? c * plane + toff[tap] : 0);
+                        sidx[i] = thr_m + (kval[i] ? c * plane + toff[tap] : 0);
                         if (++c == nch) { c = 0; ++tap; }
                     }
                 }
@@ -739,46 +749,50 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 if (c0 >= nch) { c0 -= nch; ++tap0; }
             }
         }
+        }
         if (ktiles > 0) tm_mbar_wait(accum_bar, 0, a.soft, 5, 0);
         if (tracing && warp == 2 && lane == 0) trace[6 * 64 + 0] = clock64() - t_start;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q4 = warp & 3, colq = (warp - 2) >> 2;        // 4 warps per TMEM lane quarter split the columns
-        const int oy = y0 + q4, ox = x0 + lane;
-        const bool evalid = (oy < a.Hc) && (ox < a.Wc);
         const long long HWout = (long long)a.Hout * a.Wout;
-        const long long obase = (long long)b * a.Ntot * HWout + (long long)(oy * a.out_stride + a.out_oy) * a.Wout +
-                                (ox * a.out_stride + a.out_ox);
-        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
-        for (int cg = colq; cg * 16 < ntile; cg += 4) {
-            float v[16];
-            if (ktiles > 0) {
-                tm_ld16(trow + (uint32_t)(cg * 16), v);
-                if (THREE) {
-                    float v2[16];
-                    tm_ld16(trow + (uint32_t)(a.nbox + cg * 16), v2);
+        const int ox = x0 + lane;
+        for (int m = 0; m < a.mt; ++m) {
+            const int oy = y0 + m * 4 + q4;
+            const bool evalid = (oy < a.Hc) && (ox < a.Wc);
+            const long long obase = (long long)b * a.Ntot * HWout + (long long)(oy * a.out_stride + a.out_oy) * a.Wout +
+                                    (ox * a.out_stride + a.out_ox);
+            const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(m * (THREE ? 3 : 1) * a.nbox);
+            for (int cg = colq; cg * 16 < ntile; cg += 4) {
+                float v[16];
+                if (ktiles > 0) {
+                    tm_ld16(trow + (uint32_t)(cg * 16), v);
+                    if (THREE) {
+                        float v2[16];
+                        tm_ld16(trow + (uint32_t)(a.nbox + cg * 16), v2);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += v2[j];
-                    tm_ld16(trow + 256u + (uint32_t)(cg * 16), v2);
+                        for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                        tm_ld16(trow + (uint32_t)(2 * a.nbox + cg * 16), v2);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                        for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
                 }
-            } else {
+                if (evalid) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0.f;
-            }
-            if (evalid) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = n0 + cg * 16 + j;
-                    if (cg * 16 + j < ntile) {
-                        float o = v[j];
-                        const long long off = obase + (long long)n * HWout;
-                        if (a.splits > 1) {
-                            a.partial[(long long)blockIdx.z * a.out_numel + off] = o;
-                        } else {
-                            if (a.bias) o += __ldg(a.bias + n);
-                            if (a.res) o += __ldg(a.res + off);
-                            a.out[off] = tm_act(o, a.act, a.slope);
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + cg * 16 + j;
+                        if (cg * 16 + j < ntile) {
+                            float o = v[j];
+                            const long long off = obase + (long long)n * HWout;
+                            if (a.splits > 1) {
+                                a.partial[(long long)blockIdx.z * a.out_numel + off] = o;
+                            } else {
+                                if (a.bias) o += __ldg(a.bias + n);
+                                if (a.res) o += __ldg(a.res + off);
+                                a.out[off] = tm_act(o, a.act, a.slope);
+                            }
                         }
                     }
                 }
@@ -800,11 +814,12 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 }
 
 struct SlabPlan {
-    int cs, cblocks, kt_full, ktiles, SW, SH, ox_lo, oy_lo, slab_bytes, nslab, nstages, nbox, b_tile_bytes, smem;
+    int cs, cblocks, kt_full, ktiles, SW, SH, ox_lo, oy_lo, slab_bytes, nslab, nstages, nbox, b_tile_bytes, smem, mt;
     bool ok;
 };
 // tap offsets (in gathered-tensor pixels), gather stride, channels, output channels -> tiling of the K dimension
-static SlabPlan slab_plan(const int* off_y, const int* off_x, int ntaps, int in_stride, int Cc, int N, int three) {
+// `stack` > 1 asks for that many vertically stacked tiles per CTA if everything still fits (one channel block only)
+static SlabPlan slab_plan(const int* off_y, const int* off_x, int ntaps, int in_stride, int Cc, int N, int three, int stack = 1) {
     SlabPlan p;
     memset(&p, 0, sizeof(p));
     int oxl = 0, oxh = 0, oyl = 0, oyh = 0;
@@ -844,6 +859,18 @@ static SlabPlan slab_plan(const int* off_y, const int* off_x, int ntaps, int in_
         }
     }
     if (!p.ok) return p;
+    p.mt = 1;
+    if (p.cblocks == 1) {
+        for (int mt = stack; mt > 1; --mt) {                     // taller slab, mt accumulators in TMEM
+            const int sh = (4 * mt - 1) * in_stride + (oyh - oyl) + 1;
+            const int sbytes = cdiv(p.cs * sh * p.SW * 4, 128) * 128;
+            if (mt * (three ? 3 : 1) * p.nbox > 512 || sbytes + 3 * stage > total || sh > 256) continue;
+            p.mt = mt; p.SH = sh; p.slab_bytes = sbytes;
+            p.nstages = (total - sbytes) / stage;
+            if (p.nstages > 6) p.nstages = 6;
+            break;
+        }
+    }
     p.kt_full = cdiv(p.cs * nt, 32);
     const int tail = Cc - (p.cblocks - 1) * p.cs;
     p.ktiles = (p.cblocks - 1) * p.kt_full + cdiv(tail * nt, 32);
@@ -859,7 +886,13 @@ static int launch_slab(const float* x, int B, int Cc, int Hin, int Win, const fl
     EncodeTiledFn enc = get_encode();
     CCB_REQUIRE(enc != nullptr, CCB_ERR_UNSUPPORTED, "conv_slab: cuTensorMapEncodeTiled unavailable");
     CCB_REQUIRE(ntaps <= TM_MAX_SLOTS, CCB_ERR_ARG, "conv_slab: too many taps");
-    const SlabPlan p = slab_plan(off_y, off_x, ntaps, in_stride, Cc, N, three);
+    // thin layers have thousands of short tiles: stack up to 4 of them per CTA while >= 4 CTAs per SM remain
+    int stack = 1;
+    if (splits == 1) {
+        const long long tiles = (long long)B * cdiv(Wc, 32) * cdiv(Hc, 4) * cdiv(N, 128);
+        while (stack < 4 && tiles / (stack * 2) >= 4 * 148 && cdiv(Hc, 4) >= stack * 2) stack *= 2;
+    }
+    const SlabPlan p = slab_plan(off_y, off_x, ntaps, in_stride, Cc, N, three, stack);
     CCB_REQUIRE(p.ok, CCB_ERR_UNSUPPORTED, "conv_slab: no tiling fits shared memory");
     SlabArgs a;
     memset(&a, 0, sizeof(a));
@@ -867,7 +900,8 @@ static int launch_slab(const float* x, int B, int Cc, int Hin, int Win, const fl
     a.out_stride = out_stride; a.out_oy = out_oy; a.out_ox = out_ox; a.in_stride = in_stride;
     a.ntaps = ntaps; a.cs = p.cs; a.cblocks = p.cblocks; a.kt_full = p.kt_full; a.ktiles = p.ktiles;
     a.SW = p.SW; a.SH = p.SH; a.ox_lo = p.ox_lo; a.oy_lo = p.oy_lo; a.slab_bytes = p.slab_bytes; a.slab_tx = p.cs * p.SH * p.SW * 4; a.nslab = p.nslab;
-    a.tiles_x = cdiv(Wc, 32); a.tiles_y = cdiv(Hc, 4);
+    a.mt = p.mt;
+    a.tiles_x = cdiv(Wc, 32); a.tiles_y = cdiv(Hc, 4 * p.mt);
     a.splits = splits; a.kt_per_split = cdiv(a.ktiles, splits);
     a.out_numel = out_numel; a.partial = partial;
     a.bias = bias; a.res = res; a.out = out; a.act = act; a.slope = slope; a.soft = g_tma_soft;

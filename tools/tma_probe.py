@@ -46,6 +46,8 @@ CASES = [  # B, Ci, H, W, Co, k, s, p, op
     (4, 16, 256, 832, 1, 3, 1, 1, 'wgrad'),
     (4, 128, 32, 104, 128, 3, 1, 1, 'wgrad'),
     (4, 32, 128, 416, 64, 3, 2, 1, 'wgrad'),
+    (4, 16, 250, 832, 16, 3, 1, 1, 'fprop'),     # stacked tiles with a ragged bottom
+    (4, 16, 250, 832, 16, 3, 1, 1, 'dgrad'),
 ]
 
 

@@ -677,7 +677,9 @@ bool tc_profitable(const ccb_conv_desc* d, int op) {
     int N = (op == CCB_CONV_FPROP) ? d->Co : d->Ci;
     int Cc = (op == CCB_CONV_FPROP) ? d->Ci : d->Co;
     (void)N; (void)Cc;
-    return M >= 128 && (long long)d->Ci * d->Co * d->kh * d->kw >= 64;
+    const long long wsize = (long long)d->Ci * d->Co * d->kh * d->kw;
+    // tiny feature maps (2x7, 4x13 ...) under a large weight matrix are split-K problems: one M tile, many k-tiles
+    return (M >= 128 && wsize >= 64) || (M >= 8 && wsize >= 65536);
 }
 
 static int wgrad_splits(const ccb_conv_desc* d, int& stages, int& per_split) {

@@ -132,3 +132,37 @@ class Trainer:
     def replay(self):
         self.graph.replay()
         return self.static_loss
+
+
+class HostFeeder:
+    """Pinned-host batches -> the trainer's static input buffers, one batch ahead.
+
+    The reference's DataLoader (train.py: pin_memory=True, `.to(device)` in the loop) hands the step a fresh host batch
+    every iteration.  Here batch i+1 crosses PCIe on a copy stream while step i computes; `feed(i)` waits for batch i,
+    copies it device-to-device into the static buffers the CUDA graph reads, and starts the transfer of batch i+1.
+    Every batch still crosses PCIe exactly once; only the wait is hidden."""
+
+    def __init__(self, static_inputs, batch_of):
+        self.static = list(static_inputs)                  # device tensors the (captured) step reads
+        self.batch_of = batch_of                           # i -> list of pinned host tensors, same order / shapes
+        self.stage = [[torch.empty_like(t) for t in self.static] for _ in range(2)]
+        self.stream = torch.cuda.Stream()
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.next = None
+
+    def _start(self, i):
+        self.stream.wait_stream(torch.cuda.current_stream())      # the slot's previous reader (a D2D copy) is done
+        with torch.cuda.stream(self.stream):
+            for d, h in zip(self.stage[i & 1], self.batch_of(i)):
+                d.copy_(h, non_blocking=True)
+            self.ready[i & 1].record(self.stream)
+        self.next = i
+
+    def feed(self, i, prefetch=True):
+        if self.next != i:
+            self._start(i)
+        torch.cuda.current_stream().wait_event(self.ready[i & 1])
+        for s, d in zip(self.static, self.stage[i & 1]):
+            s.copy_(d, non_blocking=True)
+        if prefetch:
+            self._start(i + 1)

@@ -178,9 +178,10 @@ def run_ours(args):
     last_loss = float(loss_host[0])
 
     out = None
+    # the profile pass runs whole (eager) steps, all-reduce included: EVERY rank must take part
+    prof = profile_pass(trainer, tgt, refs, K, Kinv) if not args.no_profile else {}
     if rank == 0:
         pk = peaks()
-        prof = profile_pass(trainer, tgt, refs, K, Kinv) if not args.no_profile else {}
         value = world * B * args.steps / (ms_total * 1e-3)
         e2e = world * B * args.steps / (ms_e2e * 1e-3)
         out = {

@@ -946,6 +946,247 @@ static int launch_slab(const float* x, int B, int Cc, int Hin, int Win, const fl
     return check_launch("conv_slab");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Direct kernel (CUDA cores, plain fp32 FMA) for THIN layers: few output channels (<= 32 per block) and a short
+// K = channels x taps.  The tensor core's tf32 MMA has K = 8 per instruction and needs 3 passes for fp32 accuracy:
+// with N = 16 an MMA carries 16 K MACs and the kernel is issue bound; one fp32 FMA per MAC on the CUDA cores is
+// faster there (and exact).  Same interface as the slab kernel: an aligned TMA slab of the input patch (zero
+// padding = OOB fill), a tap list, output written with stride / offset (DGRAD parity classes).
+//   thread -> 4 pixels (px = qx + 8 e: lanes read consecutive floats) x 8 output channels; block = 32 columns x TH rows
+//   x NG channel groups (TH * NG = 32); channels arrive in chunks of CC (one slab per chunk).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DC_THREADS = 256;
+struct DirectArgs {
+    int B, Cin, Hin, Win;
+    int Ntot, Hout, Wout, Hc, Wc;
+    int out_stride, out_oy, out_ox, in_stride;
+    int ntaps, NG, TH, CC, nchunks;
+    int SW, SH, ox_lo, oy_lo, slab_bytes, slab_tx;
+    int tiles_x, tiles_y;
+    const float* wq;               // [n-block][chunk][tap][CC][NG*8]
+    const float* bias;
+    const float* res;
+    float* out;
+    int act;
+    float slope;
+    signed char off_y[TM_MAX_SLOTS], off_x[TM_MAX_SLOTS];
+};
+
+__global__ void __launch_bounds__(DC_THREADS, 2)
+conv_direct_kernel(const __grid_constant__ CUtensorMap map_x, const DirectArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* slab = (float*)smem_raw;
+    const int n8 = a.NG * 8;
+    float* wsm = (float*)(smem_raw + a.slab_bytes);                     // [tap][CC][n8]
+    int* toff = (int*)(wsm + a.ntaps * a.CC * n8);
+    uint64_t* bar = (uint64_t*)(toff + TM_MAX_SLOTS);
+
+    const int tid = threadIdx.x;
+    const int qx = tid & 7, rest = tid >> 3;
+    const int ng = rest % a.NG, ry = rest / a.NG;
+    int t = blockIdx.x;
+    const int per_b = a.tiles_x * a.tiles_y;
+    const int b = t / per_b;
+    t -= b * per_b;
+    const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+    const int x0 = tx * 32, y0 = ty * a.TH;
+    const int nblk = blockIdx.y, n0 = nblk * n8;
+    const int s_in = a.in_stride;
+    const int xs = (x0 * s_in + a.ox_lo) & ~3;
+    const int dx0 = x0 * s_in + a.ox_lo - xs;
+    const int ys = y0 * s_in + a.oy_lo;
+    const int plane = a.SH * a.SW;
+
+    if (tid < TM_MAX_SLOTS) toff[tid] = (tid < a.ntaps) ? (a.off_y[tid] - a.oy_lo) * a.SW + (a.off_x[tid] - a.ox_lo) : 0;
+    if (tid == 0) {
+        tm_prefetch_map(&map_x);
+        tm_mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    float acc[4][8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[e][j] = 0.f;
+
+    const int thr = ry * s_in * a.SW + dx0 + qx * s_in;                  // pixel e sits 8 * e * s_in floats further
+    const int wchunk = a.ntaps * a.CC * n8;
+    const float* wq = a.wq + (long long)nblk * a.nchunks * wchunk;
+    for (int ch = 0; ch < a.nchunks; ++ch) {
+        if (tid == 0) {
+            tm_mbar_expect_tx(bar, (uint32_t)a.slab_tx);
+            tma_load_4d(slab, &map_x, bar, xs, ys, ch * a.CC, b);
+        }
+        {   // this chunk's weights (coalesced float4)
+            const float4* src = (const float4*)(wq + (long long)ch * wchunk);
+            float4* dst = (float4*)wsm;
+            for (int i = tid; i < wchunk / 4; i += DC_THREADS) dst[i] = __ldg(src + i);
+        }
+        tm_mbar_wait(bar, ch & 1, 0, 8, ch);
+        __syncthreads();
+        for (int tp = 0; tp < a.ntaps; ++tp) {
+            const float* sp = slab + toff[tp] + thr;
+            const float* wp = wsm + tp * a.CC * n8 + ng * 8;
+#pragma unroll 4
+            for (int c = 0; c < a.CC; ++c) {
+                const float i0 = sp[0], i1 = sp[8 * s_in], i2 = sp[16 * s_in], i3 = sp[24 * s_in];
+                const float4 w0 = *(const float4*)wp, w1 = *(const float4*)(wp + 4);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    acc[0][j] = fmaf(i0, wv[j], acc[0][j]);
+                    acc[1][j] = fmaf(i1, wv[j], acc[1][j]);
+                    acc[2][j] = fmaf(i2, wv[j], acc[2][j]);
+                    acc[3][j] = fmaf(i3, wv[j], acc[3][j]);
+                }
+                sp += plane;
+                wp += n8;
+            }
+        }
+        __syncthreads();                                                  // the next chunk overwrites slab and weights
+    }
+    const int oy = y0 + ry;
+    if (oy < a.Hc) {
+        const long long HWout = (long long)a.Hout * a.Wout;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int ox = x0 + qx + 8 * e;
+            if (ox >= a.Wc) continue;
+            const long long obase = (long long)b * a.Ntot * HWout + (long long)(oy * a.out_stride + a.out_oy) * a.Wout +
+                                    (ox * a.out_stride + a.out_ox);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = n0 + ng * 8 + j;
+                if (n < a.Ntot) {
+                    const long long off = obase + (long long)n * HWout;
+                    float o = acc[e][j];
+                    if (a.bias) o += __ldg(a.bias + n);
+                    if (a.res) o += __ldg(a.res + off);
+                    a.out[off] = tm_act(o, a.act, a.slope);
+                }
+            }
+        }
+    }
+}
+
+// wq[n-block][chunk][tap][cc][n8] from the conv weights (mode 0: w[n][c][tap], mode 1: w[c][n][tap]); zero padded
+struct DirectPrepArgs {
+    const float* w;
+    float* wq;
+    int N, Cc, KK, Ci, mode, ntaps, CC, nchunks, n8, nblocks;
+    signed char tap_index[TM_MAX_SLOTS];
+};
+__global__ void __launch_bounds__(256) direct_wprep_kernel(const DirectPrepArgs a) {
+    const long long total = (long long)a.nblocks * a.nchunks * a.ntaps * a.CC * a.n8;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    long long r = i;
+    const int j = (int)(r % a.n8); r /= a.n8;
+    const int cc = (int)(r % a.CC); r /= a.CC;
+    const int tp = (int)(r % a.ntaps); r /= a.ntaps;
+    const int ch = (int)(r % a.nchunks); r /= a.nchunks;
+    const int n = (int)r * a.n8 + j, c = ch * a.CC + cc;
+    float v = 0.f;
+    if (n < a.N && c < a.Cc) {
+        const int tap = a.tap_index[tp];
+        v = (a.mode == 0) ? __ldg(a.w + ((long long)n * a.Cc + c) * a.KK + tap) : __ldg(a.w + ((long long)c * a.Ci + n) * a.KK + tap);
+    }
+    a.wq[i] = v;
+}
+
+struct DirectPlan {
+    int NG, TH, CC, nchunks, SW, SH, ox_lo, oy_lo, slab_bytes, smem, n8, nblocks;
+    bool ok;
+};
+static DirectPlan direct_plan(const int* off_y, const int* off_x, int ntaps, int in_stride, int Cc, int N) {
+    DirectPlan p;
+    memset(&p, 0, sizeof(p));
+    if (ntaps < 1) return p;
+    int oxl = 0, oxh = 0, oyl = 0, oyh = 0;
+    for (int t = 0; t < ntaps; ++t) {
+        if (t == 0 || off_x[t] < oxl) oxl = off_x[t];
+        if (t == 0 || off_x[t] > oxh) oxh = off_x[t];
+        if (t == 0 || off_y[t] < oyl) oyl = off_y[t];
+        if (t == 0 || off_y[t] > oyh) oyh = off_y[t];
+    }
+    p.ox_lo = oxl; p.oy_lo = oyl;
+    p.NG = N > 16 ? 4 : (N > 8 ? 2 : 1);
+    p.TH = 32 / p.NG;
+    p.n8 = p.NG * 8;
+    p.nblocks = cdiv(N, p.n8);
+    p.SW = (31 * in_stride + (oxh - oxl) + 1 + 3 + 3) & ~3;
+    p.SH = (p.TH - 1) * in_stride + (oyh - oyl) + 1;
+    if (p.SW > 256 || p.SH > 256) return p;
+    const int per_ch = p.SH * p.SW * 4;
+    int cc = (44 * 1024) / per_ch;
+    if (cc > Cc) cc = Cc;
+    if (cc > 32) cc = 32;
+    if (cc < 1) return p;
+    p.CC = cc;
+    p.nchunks = cdiv(Cc, cc);
+    p.slab_bytes = cdiv(cc * per_ch, 128) * 128;
+    p.smem = p.slab_bytes + ntaps * cc * p.n8 * 4 + TM_MAX_SLOTS * 4 + 64;
+    p.ok = p.smem <= 100 * 1024;
+    return p;
+}
+// thin problem: few output channels, short reduction
+// measured (tools/tma_probe.py): ~17-20 TFLOP/s whatever the shape; the tensor-core kernels pass that at N = 32 with K >= 288
+static bool direct_profitable(int N, int Cc, int ntaps) {
+    const long long K = (long long)Cc * ntaps;
+    return ntaps >= 1 && K <= 1024 && (N <= 24 || K <= 160);
+}
+
+static long long direct_wq_floats(const DirectPlan& p, int ntaps) { return (long long)p.nblocks * p.nchunks * ntaps * p.CC * p.n8; }
+
+static int launch_direct(const float* x, int B, int Cc, int Hin, int Win, const float* w, int mode, int N, int KK, int Ci,
+                         const int* off_y, const int* off_x, const int* tap_index, int ntaps, int in_stride, int Hc, int Wc, int Hout,
+                         int Wout, int out_stride, int out_oy, int out_ox, const float* bias, const float* res, float* out, int act,
+                         float slope, float* work, long long work_floats, cudaStream_t st) {
+    EncodeTiledFn enc = get_encode();
+    CCB_REQUIRE(enc != nullptr, CCB_ERR_UNSUPPORTED, "conv_direct: cuTensorMapEncodeTiled unavailable");
+    const DirectPlan p = direct_plan(off_y, off_x, ntaps, in_stride, Cc, N);
+    CCB_REQUIRE(p.ok, CCB_ERR_UNSUPPORTED, "conv_direct: no tiling fits shared memory");
+    const long long wqf = direct_wq_floats(p, ntaps);
+    CCB_REQUIRE(work && wqf <= work_floats, CCB_ERR_ARG, "conv_direct: workspace too small");
+    DirectPrepArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    DirectArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int t = 0; t < TM_MAX_SLOTS; ++t) {
+        a.off_y[t] = (signed char)(t < ntaps ? off_y[t] : 0);
+        a.off_x[t] = (signed char)(t < ntaps ? off_x[t] : 0);
+        pa.tap_index[t] = (signed char)(t < ntaps ? tap_index[t] : 0);
+    }
+    pa.w = w; pa.wq = work; pa.N = N; pa.Cc = Cc; pa.KK = KK; pa.Ci = Ci; pa.mode = mode; pa.ntaps = ntaps; pa.CC = p.CC;
+    pa.nchunks = p.nchunks; pa.n8 = p.n8; pa.nblocks = p.nblocks;
+    CCB_LAUNCH(direct_wprep_kernel, dim3((unsigned)((wqf + 255) / 256)), dim3(256), 0, st, pa);
+    int rc = check_launch("conv_direct wprep");
+    if (rc) return rc;
+    a.B = B; a.Cin = Cc; a.Hin = Hin; a.Win = Win; a.Ntot = N; a.Hout = Hout; a.Wout = Wout; a.Hc = Hc; a.Wc = Wc;
+    a.out_stride = out_stride; a.out_oy = out_oy; a.out_ox = out_ox; a.in_stride = in_stride;
+    a.ntaps = ntaps; a.NG = p.NG; a.TH = p.TH; a.CC = p.CC; a.nchunks = p.nchunks;
+    a.SW = p.SW; a.SH = p.SH; a.ox_lo = p.ox_lo; a.oy_lo = p.oy_lo; a.slab_bytes = p.slab_bytes; a.slab_tx = p.CC * p.SH * p.SW * 4;
+    a.tiles_x = cdiv(Wc, 32); a.tiles_y = cdiv(Hc, p.TH);
+    a.wq = work; a.bias = bias; a.res = res; a.out = out; a.act = act; a.slope = slope;
+    alignas(64) CUtensorMap map_x;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)Cc, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)Win * 4, (cuuint64_t)Win * Hin * 4, (cuuint64_t)Win * Hin * Cc * 4};
+        cuuint32_t box[4] = {(cuuint32_t)p.SW, (cuuint32_t)p.SH, (cuuint32_t)p.CC, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CCB_REQUIRE(r == CUDA_SUCCESS, CCB_ERR_LAUNCH, "conv_direct: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+    }
+    dim3 grid(B * a.tiles_x * a.tiles_y, p.nblocks, 1);
+    cudaFuncSetAttribute(conv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    CCB_LAUNCH(conv_direct_kernel, grid, dim3(DC_THREADS), p.smem, st, map_x, a);
+    return check_launch("conv_direct");
+}
+
 // tap lists: offsets are in pixels of the gathered tensor, tap_index addresses the kh*kw weight plane
 static int fprop_taps(const ccb_conv_desc* d, int* oy, int* ox, int* tix) {
     for (int ky = 0; ky < d->kh; ++ky)
@@ -986,7 +1227,14 @@ bool tma_conv_supported(const ccb_conv_desc* d, int op) {
     return false;
 }
 
-static long long tma_wp_floats(const int* oy, const int* ox, int nt, int in_stride, int Cc, int N) {
+// does the direct (CUDA-core) kernel take this launch?  `tiles32` = number of 32-column output tiles x rows / 8 (coarse CTA count)
+static bool direct_applies(const int* oy, const int* ox, int nt, int in_stride, int Cc, int N, long long out_px) {
+    if (!direct_profitable(N, Cc, nt) || out_px < 148ll * 1024) return false;
+    return direct_plan(oy, ox, nt, in_stride, Cc, N).ok;
+}
+
+static long long tma_wp_floats(const int* oy, const int* ox, int nt, int in_stride, int Cc, int N, long long out_px) {
+    if (direct_applies(oy, ox, nt, in_stride, Cc, N, out_px)) return direct_wq_floats(direct_plan(oy, ox, nt, in_stride, Cc, N), nt);
     if (taps_aligned(ox, nt, in_stride, Cc)) {
         const int cb = Cc >= 32 ? 32 : (Cc > 8 ? 16 : 8);
         const int Kp = cdiv((nt > 0 ? nt : 1) * cdiv(Cc, cb) * cb, 32) * 32;
@@ -996,12 +1244,20 @@ static long long tma_wp_floats(const int* oy, const int* ox, int nt, int in_stri
     return p.ok ? 2ll * N * p.ktiles * 32 : -1;
 }
 
+// FPROP shapes the direct kernel takes (the dispatcher otherwise keeps thin FPROPs on the register-gather kernel)
+bool tma_direct_fprop(const ccb_conv_desc* d) {
+    int oy[TM_MAX_SLOTS], ox[TM_MAX_SLOTS], tix[TM_MAX_SLOTS];
+    if (d->kh * d->kw > TM_MAX_SLOTS) return false;
+    const int nt = fprop_taps(d, oy, ox, tix);
+    return direct_applies(oy, ox, nt, d->stride, d->Ci, d->Co, (long long)d->B * d->Ho * d->Wo);
+}
+
 long long tma_workspace_floats(const ccb_conv_desc* d, int op) {
     int oy[TM_MAX_SLOTS], ox[TM_MAX_SLOTS], tix[TM_MAX_SLOTS];
     long long wpf = 0, tiles, out_numel;
     if (op == CCB_CONV_FPROP) {
         const int nt = fprop_taps(d, oy, ox, tix);
-        wpf = tma_wp_floats(oy, ox, nt, d->stride, d->Ci, d->Co);
+        wpf = tma_wp_floats(oy, ox, nt, d->stride, d->Ci, d->Co, (long long)d->B * d->Ho * d->Wo);
         tiles = (long long)d->B * cdiv(d->Wo, 32) * cdiv(d->Ho, 4) * cdiv(d->Co, 128);
         out_numel = (long long)d->B * d->Co * d->Ho * d->Wo;
     } else {
@@ -1009,7 +1265,7 @@ long long tma_workspace_floats(const ccb_conv_desc* d, int op) {
         for (int py = 0; py < s && py < d->Hi; ++py)
             for (int px = 0; px < s && px < d->Wi; ++px) {
                 const int nt = dgrad_taps(d, py, px, oy, ox, tix);
-                const long long f = tma_wp_floats(oy, ox, nt, 1, d->Co, d->Ci);
+                const long long f = tma_wp_floats(oy, ox, nt, 1, d->Co, d->Ci, (long long)d->B * cdiv(d->Hi, s) * cdiv(d->Wi, s));
                 if (f < 0) return -1;
                 if (f > wpf) wpf = f;
             }
@@ -1034,6 +1290,9 @@ static int launch_any(const float* x, int B, int Cc, int Hin, int Win, const flo
                       const int* oy, const int* ox, const int* tix, int nt, int in_stride, int Hc, int Wc, int Hout, int Wout,
                       int out_stride, int out_oy, int out_ox, const float* bias, const float* res, float* out, int act, float slope,
                       int three, float* work, long long wp_floats, int splits, float* partial, long long out_numel, cudaStream_t st) {
+    if (splits == 1 && direct_applies(oy, ox, nt, in_stride, Cc, N, (long long)B * Hc * Wc))
+        return launch_direct(x, B, Cc, Hin, Win, w, mode, N, KK, Ci, oy, ox, tix, nt, in_stride, Hc, Wc, Hout, Wout, out_stride, out_oy,
+                             out_ox, bias, res, out, act, slope, work, wp_floats, st);
     if (taps_aligned(ox, nt, in_stride, Cc))
         return launch_tma(x, B, Cc, Hin, Win, w, mode, N, KK, Ci, oy, ox, tix, nt, Hc, Wc, Hout, Wout, out_stride, out_oy, out_ox, bias,
                           res, out, act, slope, three, work, wp_floats, splits, partial, out_numel, st);
@@ -1046,7 +1305,7 @@ int tma_fprop(const ccb_conv_desc* d, const float* x, const float* w, const floa
     int oy[TM_MAX_SLOTS], ox[TM_MAX_SLOTS], tix[TM_MAX_SLOTS];
     const int nt = fprop_taps(d, oy, ox, tix);
     const long long out_numel = (long long)d->B * d->Co * d->Ho * d->Wo;
-    const long long wpf = tma_wp_floats(oy, ox, nt, d->stride, d->Ci, d->Co);
+    const long long wpf = tma_wp_floats(oy, ox, nt, d->stride, d->Ci, d->Co, (long long)d->B * d->Ho * d->Wo);
     CCB_REQUIRE(wpf >= 0 && wpf <= work_floats, CCB_ERR_ARG, "conv_tma fprop: workspace too small");
     const long long tiles = (long long)d->B * cdiv(d->Wo, 32) * cdiv(d->Ho, 4) * cdiv(d->Co, 128);
     const int splits = tma_plan_splits(tiles, (int)(wpf / (64ll * d->Co)), out_numel, work_floats - wpf);
@@ -1066,7 +1325,7 @@ int tma_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const flo
     for (int py = 0; py < s && py < d->Hi; ++py)
         for (int px = 0; px < s && px < d->Wi; ++px) {
             const int nt = dgrad_taps(d, py, px, oy, ox, tix);
-            const long long f = tma_wp_floats(oy, ox, nt, 1, d->Co, d->Ci);
+            const long long f = tma_wp_floats(oy, ox, nt, 1, d->Co, d->Ci, (long long)d->B * cdiv(d->Hi, s) * cdiv(d->Wi, s));
             CCB_REQUIRE(f >= 0, CCB_ERR_UNSUPPORTED, "conv_tma dgrad: no tiling");
             if (f > wpf_max) wpf_max = f;
         }
@@ -1443,6 +1702,7 @@ extern "C" int ccb_debug_tma_status(unsigned int* out4) {
 namespace ccb {
 void tma_set_enabled(int) {}
 bool tma_conv_supported(const ccb_conv_desc*, int) { return false; }
+bool tma_direct_fprop(const ccb_conv_desc*) { return false; }
 long long tma_workspace_floats(const ccb_conv_desc*, int) { return 0; }
 int tma_fprop(const ccb_conv_desc*, const float*, const float*, const float*, const float*, float*, float*, long long, int,
               cudaStream_t) { return CCB_ERR_UNSUPPORTED; }

@@ -48,6 +48,18 @@ CASES = [  # B, Ci, H, W, Co, k, s, p, op
     (4, 32, 128, 416, 64, 3, 2, 1, 'wgrad'),
     (4, 16, 250, 832, 16, 3, 1, 1, 'fprop'),     # stacked tiles with a ragged bottom
     (4, 16, 250, 832, 16, 3, 1, 1, 'dgrad'),
+    (4, 16, 256, 832, 1, 3, 1, 1, 'fprop'),      # 36: thin layers for the direct kernel
+    (4, 3, 256, 832, 32, 7, 2, 3, 'fprop'),
+    (4, 17, 256, 832, 16, 1, 1, 0, 'fprop'),
+    (4, 32, 128, 416, 16, 3, 2, 1, 'convT'),
+    (4, 15, 256, 832, 16, 7, 2, 3, 'dgrad'),
+    (4, 65, 128, 416, 32, 3, 1, 1, 'dgrad'),
+    (4, 65, 128, 416, 32, 3, 1, 1, 'fprop'),
+    (4, 32, 128, 416, 32, 3, 1, 1, 'fprop'),
+    (4, 16, 128, 416, 32, 5, 2, 2, 'fprop'),
+    (2, 13, 70, 100, 20, 3, 1, 1, 'fprop'),      # 45: ragged everything (direct kernel needs out_px >= 148K: not taken)
+    (6, 13, 100, 260, 20, 3, 1, 1, 'fprop'),     # 46: ragged, large enough for the direct kernel
+    (6, 13, 100, 260, 20, 3, 2, 1, 'dgrad'),
 ]
 
 

@@ -107,15 +107,32 @@ def host_batches(nb, B, seed0):
     return out
 
 
+def _say(msg):
+    """progress line on stderr (CCB_BENCH_VERBOSE=1): which phase a rank is in when a multi-GPU run stalls"""
+    if os.environ.get('CCB_BENCH_VERBOSE'):
+        sys.stderr.write('[bench rank %s %.1fs] %s\n' % (os.environ.get('RANK', '0'), time.perf_counter() - _T0, msg))
+        sys.stderr.flush()
+
+
+_T0 = time.perf_counter()
+
+
 def run_ours(args):
     from cc_b200 import _lib, dist as cdist, pyramid
     from cc_b200.train_step import Trainer
+    wd = float(os.environ.get('CCB_BENCH_WATCHDOG', '0'))
+    if wd > 0:                                              # dump every thread's Python stack and exit instead of hanging
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True, file=sys.stderr)
+    _say('init process group')
     rank, local, world = cdist.init_from_env()
     assert world == args.gpus, 'WORLD_SIZE %d != --gpus %d (launch with torch.distributed.run)' % (world, args.gpus)
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
     B = PER_GPU_BATCH
+    _say('build trainer (+ parameter broadcast)')
     trainer = Trainer(args.cfg, dev, seed=0)
+    _say('host batches')
     hb = host_batches(4, B, seed0=1000 * rank)
     static = [torch.empty_like(t, device=dev) for t in hb[0]]
     for s, h in zip(static, hb[0]):
@@ -125,6 +142,7 @@ def run_ours(args):
 
     # one eager step to count our launches per step, then capture the step as a CUDA graph
     torch.cuda.synchronize()
+    _say('eager steps')
     pyramid.clear()
     trainer.step(tgt, refs, K, Kinv)
     c0 = _lib.lib().ccb_launch_count()
@@ -133,7 +151,9 @@ def run_ours(args):
     launches_per_step = _lib.lib().ccb_launch_count() - c0
     use_graph = not args.no_graph
     if use_graph:
+        _say('capture')
         trainer.capture(tgt, refs, K, Kinv, warmup=1)
+    _say('warm-up replays')
 
     def one_step():
         if use_graph:
@@ -145,6 +165,7 @@ def run_ours(args):
         one_step()
     # ---- value: device-resident inputs --------------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
+    _say('timed region')
     torch.cuda.synchronize(); cdist.barrier()
     if sampler:
         sampler.start()
@@ -157,6 +178,7 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     ms_total = cdist.max_over_ranks(e0.elapsed_time(e1), dev)
     # ---- e2e: host inputs, H2D + D2H inside the timed region ----------------------------------------
+    _say('e2e region')
     from cc_b200.train_step import HostFeeder
     loss_host = torch.empty(1).pin_memory()
     feeder = HostFeeder(static, lambda i: hb[i % len(hb)])
@@ -179,7 +201,9 @@ def run_ours(args):
 
     out = None
     # the profile pass runs whole (eager) steps, all-reduce included: EVERY rank must take part
+    _say('profile pass')
     prof = profile_pass(trainer, tgt, refs, K, Kinv) if not args.no_profile else {}
+    _say('done')
     if rank == 0:
         pk = peaks()
         value = world * B * args.steps / (ms_total * 1e-3)
@@ -202,8 +226,6 @@ def run_ours(args):
         out.update(prof.get('json', {}))
         if world == 1 and not args.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline(args.cfg, budget_s=25.0)
-    if world > 1:
-        torch.distributed.destroy_process_group()
     return out
 
 
@@ -391,6 +413,14 @@ def main():
     out = run_reference(args) if args.impl == 'reference' else run_ours(args)
     if out is not None:
         print(json.dumps(out))
+    sys.stdout.flush()
+    if args.impl == 'ours' and int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        # A captured CUDA graph that contains the NCCL all-reduce keeps the communicator busy: destroy_process_group()
+        # blocks forever on it (observed on 2xB200).  The result is printed; leave without the teardown.
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':

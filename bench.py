@@ -129,6 +129,7 @@ def run_ours(args):
     assert world == args.gpus, 'WORLD_SIZE %d != --gpus %d (launch with torch.distributed.run)' % (world, args.gpus)
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
+    numa_bound = cdist.bind_to_gpu_numa(local) if world > 1 else False
     B = PER_GPU_BATCH
     _say('build trainer (+ parameter broadcast)')
     trainer = Trainer(args.cfg, dev, seed=0)
@@ -182,15 +183,24 @@ def run_ours(args):
     from cc_b200.train_step import HostFeeder
     loss_host = torch.empty(1).pin_memory()
     feeder = HostFeeder(static, lambda i: hb[i % len(hb)])
+    inline = (args.feed == 'inline')                       # inline: H2D straight into the graph inputs on the compute stream
+
+    def feed(i, prefetch):
+        if inline:
+            for s_, h_ in zip(static, hb[i % len(hb)]):
+                s_.copy_(h_, non_blocking=True)
+        else:
+            feeder.feed(i, prefetch=prefetch)
+
     for i in range(2):
-        feeder.feed(i, prefetch=False)
+        feed(i, False)
         one_step()
     torch.cuda.synchronize(); cdist.barrier()
     feeder.next = None
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
-        feeder.feed(i, prefetch=(i + 1 < args.steps))       # batch i+1 crosses PCIe while step i computes
+        feed(i, i + 1 < args.steps)                        # prefetch mode: batch i+1 crosses PCIe while step i computes
         loss = one_step()
         loss_host.copy_(loss.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()          # the reference reads loss.item() every step
@@ -215,9 +225,11 @@ def run_ours(args):
             'config': {'workload': CFG_WORKLOAD[args.cfg], 'global_batch': world * B, 'per_gpu_batch': B,
                        'frame': '%dx%d' % (H, W), 'levels': NLEVELS, 'parallelism': 'dp%d' % world,
                        'conv_math': 'tcgen05 kind::tf32 x3 split precision (fp32-accurate, <=1e-4 parity)', 'cuda_graph': use_graph,
+                       'numa_bound': numa_bound,
                        'l2_policy': 'inputs and activations (~1 GB/step) exceed the 126 MB L2; no explicit flush',
-                       'e2e_input_path': 'pinned host batch -> H2D on a copy stream one step ahead (HostFeeder) -> D2D into the graph inputs; '
-                                         'all steps+copies inside the timed region'},
+                       'e2e_input_path': ('pinned host batch -> H2D on a copy stream one step ahead (HostFeeder) -> D2D into the graph inputs; '
+                                          'all steps+copies inside the timed region') if args.feed == 'prefetch' else
+                                         'pinned host batch -> H2D into the graph inputs on the compute stream'},
             'e2e': {'value': e2e, 'unit': 'triplets/s', 'h2d_bytes_per_step': in_bytes, 'd2h_bytes_per_step': 4,
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(launches_per_step * args.steps), 'gpu_launches_per_step': int(launches_per_step),
@@ -406,6 +418,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cfg', default='cfg1', choices=sorted(CFG_WORKLOAD))
+    ap.add_argument('--feed', default='prefetch', choices=['prefetch', 'inline'], help='e2e input path')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -29,6 +29,21 @@ def init_from_env(backend=None):
     return rank, local, world
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this process to the CPUs next to its GPU (NVML's ideal affinity) so that pinned host batches are allocated on
+    the GPU's NUMA node: a cross-socket H2D copy runs at a fraction of the PCIe rate (seen on the 2-GPU box: GPU1 sits
+    on NUMA node 1).  Best effort: any failure leaves the affinity unchanged."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        idx = int(vis.split(',')[local_rank]) if vis and vis.split(',')[local_rank].isdigit() else local_rank
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx))
+        return True
+    except Exception:
+        return False
+
+
 def world_size():
     return dist.get_world_size() if dist.is_initialized() else 1
 

@@ -455,7 +455,9 @@ extern "C" long long ccb_conv_workspace_floats(const ccb_conv_desc* d, int op) {
         ccb_conv_desc dp;
         long long xpf, dypf;
         if (wgrad_pad_desc(d, dp, xpf, dypf)) {
-            const long long t = xpf + dypf + tc_workspace_floats(&dp, op);
+            long long inner = tc_workspace_floats(&dp, op);
+            if (tma_wgrad_supported(&dp) && tma_wgrad_workspace_floats(&dp) > inner) inner = tma_wgrad_workspace_floats(&dp);
+            const long long t = xpf + dypf + inner;
             return t > bias_need ? t : bias_need;
         }
     }
@@ -558,7 +560,10 @@ extern "C" int ccb_conv2d_wgrad(const ccb_conv_desc* d, const float* x, const fl
     {
         ccb_conv_desc dp;
         long long xpf, dypf;
-        if (wgrad_pad_desc(d, dp, xpf, dypf) && work && xpf + dypf + tc_workspace_floats(&dp, CCB_CONV_WGRAD) <= work_floats) {
+        const bool padded = wgrad_pad_desc(d, dp, xpf, dypf);
+        const bool via_tma = padded && tma_wgrad_supported(&dp);
+        const long long inner = padded ? (via_tma ? tma_wgrad_workspace_floats(&dp) : tc_workspace_floats(&dp, CCB_CONV_WGRAD)) : 0;
+        if (padded && work && xpf + dypf + inner <= work_floats) {
             float* xp = work;
             float* dyp = work + xpf;
             CCB_LAUNCH(pad_rows_kernel, dim3((unsigned)((xpf + 255) / 256)), dim3(256), 0, stream, x, xp, (long long)d->B * d->Ci * d->Hi,
@@ -567,8 +572,12 @@ extern "C" int ccb_conv2d_wgrad(const ccb_conv_desc* d, const float* x, const fl
                        d->Wo, dp.Wo);
             rc = check_launch("conv2d_wgrad pad");
             if (rc) return rc;
-            rc = tc_wgrad(&dp, xp, dyp, dw, work + xpf + dypf, work_floats - xpf - dypf, d->impl != CCB_CONV_IMPL_TC_TF32,
-                          (cudaStream_t)stream);
+            if (via_tma)
+                rc = tma_wgrad(&dp, xp, dyp, dw, work + xpf + dypf, work_floats - xpf - dypf, d->impl != CCB_CONV_IMPL_TC_TF32,
+                               (cudaStream_t)stream);
+            else
+                rc = tc_wgrad(&dp, xp, dyp, dw, work + xpf + dypf, work_floats - xpf - dypf, d->impl != CCB_CONV_IMPL_TC_TF32,
+                              (cudaStream_t)stream);
             if (rc) return rc;
             if (db) rc = launch_bias_grad(dy, db, d->B, d->Co, d->Ho * d->Wo, work, work_floats, (cudaStream_t)stream);
             return rc;

@@ -1218,13 +1218,33 @@ static bool taps_aligned(const int* ox, int nt, int in_stride, int Cc) {
     return true;
 }
 
-// Which problems the TMA-fed kernels take: 16-byte aligned rows of the gathered tensor, at least one full 32-column tile.
+// TMA needs 16-byte aligned rows.  A small gathered tensor whose width is not a multiple of 4 (26, 13 ...) is first
+// copied into rows padded with zeros (exactly what the convolution's own zero padding would read there).
+__global__ void __launch_bounds__(256) tma_pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int W,
+                                                           int Wp) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= rows * Wp) return;
+    const long long r = i / Wp;
+    const int x = (int)(i - r * Wp);
+    dst[i] = (x < W) ? __ldg(src + r * W + x) : 0.f;
+}
+// floats of the padded copy of the gathered tensor (0: rows are aligned already, -1: too large to copy)
+static long long tma_pad_floats(const ccb_conv_desc* d, int op) {
+    const int W = (op == CCB_CONV_FPROP) ? d->Wi : d->Wo;
+    if (W % 4 == 0) return 0;
+    const long long f = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Ci * d->Hi * ((W + 3) & ~3) : (long long)d->B * d->Co * d->Ho * ((W + 3) & ~3);
+    return f <= (4ll << 20) ? f : -1;
+}
+
+// Which problems the TMA-fed kernels take: rows of the gathered tensor 16-byte aligned (or small enough to pad), output
+// rows that fill most of a 32-column tile.
 bool tma_conv_supported(const ccb_conv_desc* d, int op) {
     if (!g_tma_enabled || get_encode() == nullptr) return false;
     if (d->kh != d->kw || d->kh * d->kw > TM_MAX_SLOTS) return false;
-    if (op == CCB_CONV_FPROP) return (d->stride == 1 || d->stride == 2) && (d->Wi % 4 == 0) && d->Wo >= 32;
-    if (op == CCB_CONV_DGRAD) return (d->Wo % 4 == 0) && cdiv(d->Wi, d->stride) >= 32;
-    return false;
+    if (op != CCB_CONV_FPROP && op != CCB_CONV_DGRAD) return false;
+    if (tma_pad_floats(d, op) < 0) return false;
+    if (op == CCB_CONV_FPROP) return (d->stride == 1 || d->stride == 2) && d->Wo >= 20;
+    return cdiv(d->Wi, d->stride) >= 20;
 }
 
 // does the direct (CUDA-core) kernel take this launch?  `tiles32` = number of 32-column output tiles x rows / 8 (coarse CTA count)
@@ -1273,7 +1293,9 @@ long long tma_workspace_floats(const ccb_conv_desc* d, int op) {
         out_numel = (long long)d->B * d->Ci * d->Hi * d->Wi;
     }
     if (wpf < 0) return -1;
-    return wpf + (tiles < 148 ? 8 * out_numel : 0);      // weights + room for up to 8 split-K partials
+    const long long padf = tma_pad_floats(d, op);
+    if (padf < 0) return -1;
+    return padf + wpf + (tiles < 148 ? 8 * out_numel : 0);      // padded copy + weights + room for up to 8 split-K partials
 }
 
 static int tma_plan_splits(long long tiles, int ktiles, long long out_numel, long long part_floats) {
@@ -1306,10 +1328,18 @@ int tma_fprop(const ccb_conv_desc* d, const float* x, const float* w, const floa
     const int nt = fprop_taps(d, oy, ox, tix);
     const long long out_numel = (long long)d->B * d->Co * d->Ho * d->Wo;
     const long long wpf = tma_wp_floats(oy, ox, nt, d->stride, d->Ci, d->Co, (long long)d->B * d->Ho * d->Wo);
-    CCB_REQUIRE(wpf >= 0 && wpf <= work_floats, CCB_ERR_ARG, "conv_tma fprop: workspace too small");
+    const long long padf = tma_pad_floats(d, CCB_CONV_FPROP);
+    CCB_REQUIRE(wpf >= 0 && padf >= 0 && padf + wpf <= work_floats, CCB_ERR_ARG, "conv_tma fprop: workspace too small");
+    int Wi = d->Wi;
+    if (padf > 0) {                                              // narrow unaligned map: padded copy first
+        Wi = (d->Wi + 3) & ~3;
+        CCB_LAUNCH(tma_pad_rows_kernel, dim3((unsigned)((padf + 255) / 256)), dim3(256), 0, st, x, work, (long long)d->B * d->Ci * d->Hi,
+                   d->Wi, Wi);
+        x = work; work += padf; work_floats -= padf;
+    }
     const long long tiles = (long long)d->B * cdiv(d->Wo, 32) * cdiv(d->Ho, 4) * cdiv(d->Co, 128);
     const int splits = tma_plan_splits(tiles, (int)(wpf / (64ll * d->Co)), out_numel, work_floats - wpf);
-    int rc = launch_any(x, d->B, d->Ci, d->Hi, d->Wi, w, 0, d->Co, nt, d->Ci, oy, ox, tix, nt, d->stride, d->Ho, d->Wo, d->Ho, d->Wo, 1,
+    int rc = launch_any(x, d->B, d->Ci, d->Hi, Wi, w, 0, d->Co, nt, d->Ci, oy, ox, tix, nt, d->stride, d->Ho, d->Wo, d->Ho, d->Wo, 1,
                         0, 0, bias, res, y, d->act, d->slope, three, work, wpf, splits, work + wpf, out_numel, st);
     if (rc || splits == 1) return rc;
     launch_splitk_reduce(work + wpf, y, bias, res, out_numel, splits, d->Ho * d->Wo, d->Co, d->act, d->slope, st);
@@ -1329,14 +1359,22 @@ int tma_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const flo
             CCB_REQUIRE(f >= 0, CCB_ERR_UNSUPPORTED, "conv_tma dgrad: no tiling");
             if (f > wpf_max) wpf_max = f;
         }
-    CCB_REQUIRE(wpf_max <= work_floats, CCB_ERR_ARG, "conv_tma dgrad: workspace too small");
+    const long long padf = tma_pad_floats(d, CCB_CONV_DGRAD);
+    CCB_REQUIRE(padf >= 0 && padf + wpf_max <= work_floats, CCB_ERR_ARG, "conv_tma dgrad: workspace too small");
+    int Wo = d->Wo;
+    if (padf > 0) {
+        Wo = (d->Wo + 3) & ~3;
+        CCB_LAUNCH(tma_pad_rows_kernel, dim3((unsigned)((padf + 255) / 256)), dim3(256), 0, st, dy, work, (long long)d->B * d->Co * d->Ho,
+                   d->Wo, Wo);
+        dy = work; work += padf; work_floats -= padf;
+    }
     const long long tiles = (long long)d->B * cdiv(cdiv(d->Wi, s), 32) * cdiv(cdiv(d->Hi, s), 4) * cdiv(d->Ci, 128);
     const int splits = tma_plan_splits(tiles, (int)(wpf_max / (64ll * d->Ci)), out_numel, work_floats - wpf_max);
     for (int py = 0; py < s && py < d->Hi; ++py)
         for (int px = 0; px < s && px < d->Wi; ++px) {
             const int nt = dgrad_taps(d, py, px, oy, ox, tix);
             const int Hc = (d->Hi - py + s - 1) / s, Wc = (d->Wi - px + s - 1) / s;
-            int rc = launch_any(dy, d->B, d->Co, d->Ho, d->Wo, w, 1, d->Ci, d->kh * d->kw, d->Ci, oy, ox, tix, nt, 1, Hc, Wc, d->Hi, d->Wi,
+            int rc = launch_any(dy, d->B, d->Co, d->Ho, Wo, w, 1, d->Ci, d->kh * d->kw, d->Ci, oy, ox, tix, nt, 1, Hc, Wc, d->Hi, d->Wi,
                                 s, py, px, bias, res, dx, d->act, d->slope, three, work, wpf_max, splits, work + wpf_max, out_numel, st);
             if (rc) return rc;
         }
@@ -1628,7 +1666,7 @@ static bool wgrad_plan(const ccb_conv_desc* d, int three, SlabWgradArgs& a, int&
 bool tma_wgrad_supported(const ccb_conv_desc* d) {
     if (!g_tma_enabled || get_encode() == nullptr) return false;
     if (d->kh != d->kw || (d->stride != 1 && d->stride != 2)) return false;
-    if ((d->Wi % 4) || (d->Wo % 4) || d->Wo < 32) return false;
+    if ((d->Wi % 4) || (d->Wo % 4) || d->Wo < 20) return false;
     SlabWgradArgs a;
     int smem;
     return wgrad_plan(d, 1, a, smem);

@@ -60,6 +60,14 @@ CASES = [  # B, Ci, H, W, Co, k, s, p, op
     (2, 13, 70, 100, 20, 3, 1, 1, 'fprop'),      # 45: ragged everything (direct kernel needs out_px >= 148K: not taken)
     (6, 13, 100, 260, 20, 3, 1, 1, 'fprop'),     # 46: ragged, large enough for the direct kernel
     (6, 13, 100, 260, 20, 3, 2, 1, 'dgrad'),
+    (4, 512, 8, 26, 512, 3, 1, 1, 'fprop'),      # 48: narrow maps (W = 26): padded rows
+    (4, 512, 8, 26, 512, 3, 1, 1, 'dgrad'),
+    (4, 512, 8, 26, 512, 3, 1, 1, 'wgrad'),
+    (4, 256, 16, 52, 512, 3, 2, 1, 'dgrad'),
+    (4, 256, 16, 52, 512, 3, 2, 1, 'wgrad'),
+    (2, 24, 9, 22, 40, 3, 1, 1, 'fprop'),        # 53: small ragged narrow map
+    (2, 24, 9, 22, 40, 3, 1, 1, 'dgrad'),
+    (2, 24, 9, 22, 40, 3, 1, 1, 'wgrad'),
 ]
 
 

@@ -315,9 +315,49 @@ def profile_pass(trainer, tgt, refs, K, Kinv, steps=2):
         js['roofline_warploss'] = {'bound': 'hbm', 'kernel': 'photo_fwd+photo_bwd (fused warp+SSIM+loss)', 'achieved': ach,
                                    'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'], 'traffic': None,
                                    'share_of_step': photo_ms / total, 'peak_source': pk['source']}
+    try:
+        js['roofline_kernel'] = single_kernel_roofline(pk)
+    except Exception as exc:                               # never lose the bench line over the side measurement
+        js['roofline_kernel'] = {'error': repr(exc)[:200]}
     js['kernel_shares'] = {k: round(v['ms'] / total, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]['ms'])[:8]}
     js['profiled_step_ms'] = total / steps
     return {'json': js}
+
+
+def single_kernel_roofline(pk, iters=20):
+    """The heaviest single kernel of the step, alone: conv_slab_kernel on DispResNet6's 7x7 32->32 layer (b4, 128x416).
+    Duration = CUDA events around `iters` launches on the launching stream (inputs 27 MB + outputs 27 MB per launch,
+    weights re-prepared every launch as in the step); DRAM traffic = the committed ncu --set full capture of the same
+    launch (profiles/r01_ncu_final_key_metrics.json), null if that file is absent."""
+    from cc_b200 import nn as cnn
+    dev = torch.device('cuda', torch.cuda.current_device())
+    B, C, Hh, Ww, k = PER_GPU_BATCH, 32, H // 2, W // 2, 7
+    x = torch.randn(B, C, Hh, Ww, device=dev)
+    w = torch.randn(C, C, k, k, device=dev) * 0.05
+    b = torch.zeros(C, device=dev)
+    with torch.no_grad():
+        for _ in range(3):
+            cnn.conv2d(x, w, b, None, 1, 3, 'relu')
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            cnn.conv2d(x, w, b, None, 1, 3, 'relu')
+        e1.record()
+        torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    flops = 2.0 * B * C * C * k * k * Hh * Ww
+    ach = flops / (us * 1e-6) / 1e12
+    traffic = None
+    try:
+        km = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_final_key_metrics.json')))['slab']
+        unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        traffic = sum(float(km[m][0]) * unit[km[m][1]] for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+    except Exception:
+        pass
+    return {'bound': 'tensor', 'kernel': 'conv_slab_kernel<3xTF32> + wprep (7x7 32->32 fprop, b%d %dx%d)' % (B, Hh, Ww),
+            'achieved': ach, 'peak': pk['tensor_burst'], 'unit': 'TFLOP/s', 'frac': ach / pk['tensor_burst'],
+            'us_per_launch': us, 'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': 2.0 * B * C * Hh * Ww * 4,
+            'traffic': traffic, 'peak_source': pk['source'] + ' bf16 burst (kernel timed alone); 3 tf32 passes: ceiling = peak / 6'}
 
 
 # ---------------------------------------------------------------------------------------------------

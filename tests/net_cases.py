@@ -120,6 +120,48 @@ def case_conv_tc(device):
         cnn.CONV_IMPL = saved
 
 
+def case_conv_tma_family(device):
+    """The TMA-fed kernels at sizes that reach every dispatch branch (conv_tma.cu): the CUDA-core direct kernel (thin
+    layers, needs >= 148 K output pixels), stacked slab tiles with a ragged bottom, stride-2 slabs, narrow maps through
+    padded rows, aligned 1x1.  Checked against torch fp64 AND against the register-gather kernels (debug flag 8 turns
+    the whole family off): two independent implementations of the same convolution.  GPU only."""
+    from cc_b200 import _lib
+    g = torch.Generator().manual_seed(11)
+    shapes = [(6, 13, 100, 260, 20, 3, 1, 1),     # direct kernel: fprop + dgrad, ragged channels / rows / columns
+              (4, 15, 256, 832, 16, 7, 2, 3),     # direct kernel, stride 2 (PoseNet conv1)
+              (4, 16, 252, 832, 1, 3, 1, 1),      # direct kernel, one output channel (disparity head)
+              (4, 32, 126, 416, 32, 3, 1, 1),     # slab dgrad with stacked tiles and a ragged bottom; gather fprop
+              (2, 160, 12, 36, 72, 3, 1, 1),      # slab: several channel blocks, column tail
+              (2, 24, 9, 22, 40, 3, 1, 1),        # narrow unaligned map: padded rows (fprop, dgrad, wgrad)
+              (2, 40, 16, 64, 136, 1, 1, 0)]      # aligned 1x1: per-tap TMA boxes, N > 128
+    saved = cnn.CONV_IMPL
+    lib = _lib.lib()
+    try:
+        cnn.CONV_IMPL = _lib.IMPL_TC
+        for (B, Ci, H, W, Co, k, s, p) in shapes:
+            tag = f'tma family {Ci}->{Co} k{k} s{s} {H}x{W}'
+            x = torch.randn(B, Ci, H, W, generator=g).to(device).requires_grad_(True)
+            w = (torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5).to(device).requires_grad_(True)
+            b = torch.randn(Co, generator=g).to(device).requires_grad_(True)
+            xd, wd, bd = [t.detach().double().requires_grad_(True) for t in (x, w, b)]
+            zd = F.conv2d(xd, wd, bd, s, p)
+            wt = _wts(zd.shape, 9, device)
+            gd = torch.autograd.grad((zd * wt.double()).sum(), [xd, wd, bd])
+            outs = {}
+            for flag in (0, 8):
+                lib.ccb_debug_tc_swap_strides(flag)
+                y = cnn.conv2d(x, w, b, None, s, p, None, 0.2)
+                gx, gw, gb = torch.autograd.grad((y * wt).sum(), [x, w, b])
+                outs[flag] = (y.detach(), gx, gw, gb)
+                for got, ref, what in zip(outs[flag], (zd,) + tuple(gd), ('fprop', 'dgrad', 'wgrad', 'bias grad')):
+                    assert_close(got, ref, 1e-4, f'{tag} flag {flag} {what}')
+            for a_, b_, what in zip(outs[0], outs[8], ('fprop', 'dgrad', 'wgrad', 'bias grad')):
+                assert_close(a_, b_, 1e-4, f'{tag} TMA family vs gather kernels {what}')
+    finally:
+        lib.ccb_debug_tc_swap_strides(0)
+        cnn.CONV_IMPL = saved
+
+
 def case_bn_upsample(device):
     g = torch.Generator().manual_seed(1)
     x = torch.randn(3, 6, 5, 7, generator=g).to(device).requires_grad_(True)

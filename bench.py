@@ -463,10 +463,15 @@ def main():
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
-    out = run_reference(args) if args.impl == 'reference' else run_ours(args)
-    if out is not None:
-        print(json.dumps(out))
+    # Contract: rank 0 prints ONE JSON line on stdout.  Libraries chat on fd 1 (NCCL prints its version banner there):
+    # park the real stdout, point fd 1 at stderr for the duration of the run, write the line to the real one at the end.
     sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = run_reference(args) if args.impl == 'reference' else run_ours(args)
+    sys.stdout.flush()
+    if out is not None:
+        os.write(real_stdout, (json.dumps(out) + '\n').encode())
     if args.impl == 'ours' and int(os.environ.get('WORLD_SIZE', '1')) > 1:
         # A captured CUDA graph that contains the NCCL all-reduce keeps the communicator busy: destroy_process_group()
         # blocks forever on it (observed on 2xB200).  The result is printed; leave without the teardown.

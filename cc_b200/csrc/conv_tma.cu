@@ -1726,6 +1726,58 @@ int tma_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw
 
 }  // namespace ccb
 
+// Host-side tiling decisions of the TMA-fed family for one problem, without launching anything (and without needing a
+// driver): lets the CPU test-suite sweep every layer shape of the four networks and check the invariants the kernels
+// rely on (shared memory, TMEM columns, K coverage, TMA box limits).
+//   op FPROP / DGRAD (parity class py, px): out = {kind, cs, cblocks, kt_full, ktiles, SW, SH, slab_bytes, nslab, nstages,
+//       nbox, smem, mt, ntaps, span_x, span_y}   kind: 2 slab, 3 aligned per-tap TMA, 4 direct (then cs = CC, cblocks = nchunks,
+//       kt_full = NG, ktiles = TH, nbox = n8, mt = n-blocks), -1 no tiling
+//   op WGRAD: out = {kind 5 / -1, cwid, cblocks, tpt, tgroups, SW, SH, slab_bytes, 1, nstages, nbox, smem, splits, KK, dx0, stages}
+extern "C" int ccb_debug_conv_plan(const ccb_conv_desc* d, int op, int py, int px, int* out16) {
+    using namespace ccb;
+    if (!d || !out16 || d->kh != d->kw || d->kh * d->kw > TM_MAX_SLOTS) return CCB_ERR_ARG;
+    for (int i = 0; i < 16; ++i) out16[i] = 0;
+    if (op == CCB_CONV_WGRAD) {
+        SlabWgradArgs a;
+        memset(&a, 0, sizeof(a));
+        int smem = 0;
+        if (!wgrad_plan(d, 1, a, smem)) { out16[0] = -1; return CCB_OK; }
+        const int v[16] = {5, a.cwid, a.cblocks, a.tpt, a.tgroups, a.SW, a.SH, a.slab_bytes, 1, a.nstages, a.nbox, smem, a.splits,
+                           d->kh * d->kw, a.dx0, a.stages};
+        for (int i = 0; i < 16; ++i) out16[i] = v[i];
+        return CCB_OK;
+    }
+    int oy[TM_MAX_SLOTS], ox[TM_MAX_SLOTS], tix[TM_MAX_SLOTS];
+    int nt, in_stride, Cc, N;
+    long long out_px;
+    if (op == CCB_CONV_FPROP) {
+        nt = fprop_taps(d, oy, ox, tix); in_stride = d->stride; Cc = d->Ci; N = d->Co;
+        out_px = (long long)d->B * d->Ho * d->Wo;
+    } else {
+        nt = dgrad_taps(d, py, px, oy, ox, tix); in_stride = 1; Cc = d->Co; N = d->Ci;
+        out_px = (long long)d->B * cdiv(d->Hi, d->stride) * cdiv(d->Wi, d->stride);
+    }
+    int sx = 0, sy = 0;
+    for (int t = 0; t < nt; ++t)
+        for (int u = 0; u < nt; ++u) {
+            if (ox[t] - ox[u] > sx) sx = ox[t] - ox[u];
+            if (oy[t] - oy[u] > sy) sy = oy[t] - oy[u];
+        }
+    out16[13] = nt; out16[14] = sx; out16[15] = sy;
+    if (direct_applies(oy, ox, nt, in_stride, Cc, N, out_px)) {
+        const DirectPlan p = direct_plan(oy, ox, nt, in_stride, Cc, N);
+        const int v[13] = {4, p.CC, p.nchunks, p.NG, p.TH, p.SW, p.SH, p.slab_bytes, 1, 1, p.n8, p.smem, p.nblocks};
+        for (int i = 0; i < 13; ++i) out16[i] = v[i];
+        return CCB_OK;
+    }
+    if (taps_aligned(ox, nt, in_stride, Cc)) { out16[0] = 3; return CCB_OK; }
+    const SlabPlan p = slab_plan(oy, ox, nt, in_stride, Cc, N, 1, 4);
+    if (!p.ok) { out16[0] = -1; return CCB_OK; }
+    const int v[13] = {2, p.cs, p.cblocks, p.kt_full, p.ktiles, p.SW, p.SH, p.slab_bytes, p.nslab, p.nstages, p.nbox, p.smem, p.mt};
+    for (int i = 0; i < 13; ++i) out16[i] = v[i];
+    return CCB_OK;
+}
+
 extern "C" int ccb_debug_tma_status(unsigned int* out4) {
     if (!out4) return CCB_ERR_ARG;
     unsigned int zero[4] = {0, 0, 0, 0};
@@ -1752,6 +1804,10 @@ int tma_wgrad(const ccb_conv_desc*, const float*, const float*, float*, float*, 
     return CCB_ERR_UNSUPPORTED;
 }
 }  // namespace ccb
+extern "C" int ccb_debug_conv_plan(const ccb_conv_desc*, int, int, int, int* out16) {
+    if (out16) out16[0] = -1;
+    return CCB_OK;
+}
 extern "C" int ccb_debug_tma_status(unsigned int* out4) {
     if (out4) out4[0] = out4[1] = out4[2] = out4[3] = 0;
     return CCB_OK;

@@ -239,6 +239,10 @@ void ccb_debug_tc_swap_strides(int swap);
  * out4 = {role (0 = none; 1 producer/empty, 2 mma/tma_full, 3 mma/split_full, 4 split/tma_full, 5 epilogue/accum),
  * k-iteration, blockIdx.x, blockIdx.z} */
 int ccb_debug_tma_status(unsigned int* out4);
+/* host-side tiling of the TMA-fed convolution family for one problem (no launch, no driver needed; unit tests):
+ * op FPROP / DGRAD (parity class py, px) -> out16 = {kind (2 slab, 3 aligned TMA, 4 direct, -1 none), ...}, WGRAD -> {5, ...};
+ * field meaning in conv_tma.cu */
+int ccb_debug_conv_plan(const ccb_conv_desc* d, int op, int py, int px, int* out16);
 
 /* Back2Future operators (models/back2future.py).
  * corr81: cost volume of correlate() :15-25 (third-party spatial_correlation_sample, kernel 1, patch 9,

@@ -315,10 +315,16 @@ def profile_pass(trainer, tgt, refs, K, Kinv, steps=2):
         js['roofline_warploss'] = {'bound': 'hbm', 'kernel': 'photo_fwd+photo_bwd (fused warp+SSIM+loss)', 'achieved': ach,
                                    'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'], 'traffic': None,
                                    'share_of_step': photo_ms / total, 'peak_source': pk['source']}
+    # `roofline` = the heaviest single kernel, timed alone (spec); the aggregated convolution family moves to
+    # `roofline_family` (its share of the step is what explains the headline)
     try:
-        js['roofline_kernel'] = single_kernel_roofline(pk)
+        single = single_kernel_roofline(pk)
+        if 'roofline' in js:
+            js['roofline_family'] = js['roofline']
+            single['family_share_of_step'] = js['roofline']['share_of_step']
+        js['roofline'] = single
     except Exception as exc:                               # never lose the bench line over the side measurement
-        js['roofline_kernel'] = {'error': repr(exc)[:200]}
+        js['roofline_kernel_error'] = repr(exc)[:200]
     js['kernel_shares'] = {k: round(v['ms'] / total, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]['ms'])[:8]}
     js['profiled_step_ms'] = total / steps
     return {'json': js}
@@ -354,7 +360,15 @@ def single_kernel_roofline(pk, iters=20):
         traffic = sum(float(km[m][0]) * unit[km[m][1]] for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
     except Exception:
         pass
+    share = None
+    try:
+        for line in open(os.path.join(ROOT, 'profiles', 'r01_launches_final_summary.txt')):
+            if line.startswith('conv_slab_kernel'):
+                share = float(line.split('%')[0].split()[-1]) / 100.0
+    except Exception:
+        pass
     return {'bound': 'tensor', 'kernel': 'conv_slab_kernel<3xTF32> + wprep (7x7 32->32 fprop, b%d %dx%d)' % (B, Hh, Ww),
+            'share_of_step': share, 'share_source': 'all conv_slab_kernel launches of one step, ncu launch list (profiles/r01_launches_final_summary.txt)',
             'achieved': ach, 'peak': pk['tensor_burst'], 'unit': 'TFLOP/s', 'frac': ach / pk['tensor_burst'],
             'us_per_launch': us, 'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': 2.0 * B * C * Hh * Ww * 4,
             'traffic': traffic, 'peak_source': pk['source'] + ' bf16 burst (kernel timed alone); 3 tf32 passes: ceiling = peak / 6'}

@@ -165,15 +165,6 @@ __device__ __forceinline__ uint64_t tm_desc(uint32_t saddr, uint32_t lbo_bytes, 
     d |= (uint64_t)layout << 61;
     return d;
 }
-// four consecutive floats starting `al` (0..3) floats past the 16-byte aligned address p
-__device__ __forceinline__ float4 ld_shift4(const float* p, int al) {
-    const float4 a = *(const float4*)p;
-    if (al == 0) return a;
-    const float4 b = *(const float4*)(p + 4);
-    if (al == 1) return make_float4(a.y, a.z, a.w, b.x);
-    if (al == 2) return make_float4(a.z, a.w, b.x, b.y);
-    return make_float4(a.w, b.x, b.y, b.z);
-}
 __device__ __forceinline__ float4 tf32_rest4(const float4 v) {
     float4 l;
     l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);

@@ -32,6 +32,8 @@ PER_GPU_BATCH = 4
 CFG_WORKLOAD = {
     'cfg1': 'cfg1: DispResNet6+PoseNetB6 depth/pose step, 256x832 b4/GPU, 6 pyramid levels '
             '(photometric_reconstruction_loss + edge-aware smoothness, fwd+bwd+Adam)',
+    'cfg2': 'cfg2: Back2Future flow step, 256x832 b4/GPU, 6 levels (photometric_flow_loss + SSIM + edge-aware smoothness, '
+            'fwd+bwd+Adam)',
     'cfg3': 'cfg3: full CC joint step (Disp+Pose+Mask+Flow, 5 losses), 256x832 b4/GPU, 6 levels, fwd+bwd+Adam',
 }
 
@@ -117,33 +119,22 @@ def _say(msg):
 _T0 = time.perf_counter()
 
 
-def run_ours(args):
+def measure_cfg(cfg, args, dev, rank, local, world, steps, full):
+    """One configuration: device-resident graph-replay timing (`value`), host-fed timing (`e2e`), and - when
+    `full` - the eager profile pass (kernel shares + roofline objects).  Returns a dict of raw numbers."""
     from cc_b200 import _lib, dist as cdist, pyramid
-    from cc_b200.train_step import Trainer
-    wd = float(os.environ.get('CCB_BENCH_WATCHDOG', '0'))
-    if wd > 0:                                              # dump every thread's Python stack and exit instead of hanging
-        import faulthandler
-        faulthandler.dump_traceback_later(wd, exit=True, file=sys.stderr)
-    _say('init process group')
-    rank, local, world = cdist.init_from_env()
-    assert world == args.gpus, 'WORLD_SIZE %d != --gpus %d (launch with torch.distributed.run)' % (world, args.gpus)
-    dev = torch.device('cuda', local)
-    torch.cuda.set_device(dev)
-    numa_bound = cdist.bind_to_gpu_numa(local) if world > 1 else False
+    from cc_b200.train_step import Trainer, HostFeeder
     B = PER_GPU_BATCH
-    _say('build trainer (+ parameter broadcast)')
-    trainer = Trainer(args.cfg, dev, seed=0)
-    _say('host batches')
+    _say('%s: build trainer (+ parameter broadcast)' % cfg)
+    trainer = Trainer(cfg, dev, seed=0)
     hb = host_batches(4, B, seed0=1000 * rank)
     static = [torch.empty_like(t, device=dev) for t in hb[0]]
     for s, h in zip(static, hb[0]):
         s.copy_(h)
     tgt, refs, K, Kinv = static[0], static[1:5], static[5], static[6]
     in_bytes = sum(t.numel() * 4 for t in hb[0])
-
-    # one eager step to count our launches per step, then capture the step as a CUDA graph
     torch.cuda.synchronize()
-    _say('eager steps')
+    _say('%s: eager steps' % cfg)
     pyramid.clear()
     trainer.step(tgt, refs, K, Kinv)
     c0 = _lib.lib().ccb_launch_count()
@@ -152,9 +143,8 @@ def run_ours(args):
     launches_per_step = _lib.lib().ccb_launch_count() - c0
     use_graph = not args.no_graph
     if use_graph:
-        _say('capture')
+        _say('%s: capture' % cfg)
         trainer.capture(tgt, refs, K, Kinv, warmup=1)
-    _say('warm-up replays')
 
     def one_step():
         if use_graph:
@@ -162,25 +152,25 @@ def run_ours(args):
         pyramid.clear()
         return trainer.step(tgt, refs, K, Kinv)[0]
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         one_step()
     # ---- value: device-resident inputs --------------------------------------------------------------
-    sampler = ClockSampler(local) if rank == 0 else None
-    _say('timed region')
+    sampler = ClockSampler(local) if (rank == 0 and full) else None
+    _say('%s: timed region' % cfg)
     torch.cuda.synchronize(); cdist.barrier()
     if sampler:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = one_step()
     e1.record()
     torch.cuda.synchronize(); cdist.barrier()
     clocks = sampler.stop() if sampler else None
     ms_total = cdist.max_over_ranks(e0.elapsed_time(e1), dev)
     # ---- e2e: host inputs, H2D + D2H inside the timed region ----------------------------------------
-    _say('e2e region')
-    from cc_b200.train_step import HostFeeder
+    _say('%s: e2e region' % cfg)
     loss_host = torch.empty(1).pin_memory()
     feeder = HostFeeder(static, lambda i: hb[i % len(hb)])
     inline = (args.feed == 'inline')                       # inline: H2D straight into the graph inputs on the compute stream
@@ -199,43 +189,85 @@ def run_ours(args):
     feeder.next = None
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for i in range(args.steps):
-        feed(i, i + 1 < args.steps)                        # prefetch mode: batch i+1 crosses PCIe while step i computes
+    for i in range(steps):
+        feed(i, i + 1 < steps)                             # prefetch mode: batch i+1 crosses PCIe while step i computes
         loss = one_step()
         loss_host.copy_(loss.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()          # the reference reads loss.item() every step
     f1.record()
     torch.cuda.synchronize(); cdist.barrier()
     ms_e2e = cdist.max_over_ranks(f0.elapsed_time(f1), dev)
-    last_loss = float(loss_host[0])
-
-    out = None
+    res = dict(ms_total=ms_total, ms_e2e=ms_e2e, steps=steps, warm=warm, launches_per_step=int(launches_per_step),
+               in_bytes=in_bytes, loss=float(loss_host[0]), clocks=clocks, use_graph=use_graph, prof={})
     # the profile pass runs whole (eager) steps, all-reduce included: EVERY rank must take part
-    _say('profile pass')
-    prof = profile_pass(trainer, tgt, refs, K, Kinv) if not args.no_profile else {}
+    if full and not args.no_profile:
+        _say('%s: profile pass' % cfg)
+        res['prof'] = profile_pass(trainer, tgt, refs, K, Kinv)
+    del trainer, feeder
+    pyramid.clear()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args):
+    from cc_b200 import dist as cdist
+    wd = float(os.environ.get('CCB_BENCH_WATCHDOG', '0'))
+    if wd > 0:                                              # dump every thread's Python stack and exit instead of hanging
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True, file=sys.stderr)
+    _say('init process group')
+    rank, local, world = cdist.init_from_env()
+    assert world == args.gpus, 'WORLD_SIZE %d != --gpus %d (launch with torch.distributed.run)' % (world, args.gpus)
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    numa_bound = cdist.bind_to_gpu_numa(local) if world > 1 else False
+    B = PER_GPU_BATCH
+    m = measure_cfg(args.cfg, args, dev, rank, local, world, args.steps, full=True)
+    # the other BASELINE.json single-GPU configurations ride along as extra keys (N=1 only: scaling runs stay short)
+    side = {}
+    if world == 1 and not args.no_side_configs:
+        for c in ('cfg1', 'cfg2', 'cfg3'):
+            if c != args.cfg:
+                side[c] = measure_cfg(c, args, dev, rank, local, world, max(5, min(args.steps, 10)), full=False)
+    ref_gpu = None
+    if world == 1 and not args.no_reference_gpu:
+        _say('reference on the GPU')
+        try:
+            ref_gpu = reference_gpu(args.cfg, dev)
+        except Exception as exc:                            # context number only: never lose the bench line over it
+            ref_gpu = {'error': repr(exc)[:300]}
     _say('done')
+    out = None
     if rank == 0:
         pk = peaks()
-        value = world * B * args.steps / (ms_total * 1e-3)
-        e2e = world * B * args.steps / (ms_e2e * 1e-3)
+        tps = lambda ms, k: world * B * k / (ms * 1e-3)
         out = {
-            'metric': 'train-step triplets/sec at 256x832x6lvl', 'value': value, 'unit': 'triplets/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps,
+            'metric': 'train-step triplets/sec at 256x832x6lvl', 'value': tps(m['ms_total'], m['steps']), 'unit': 'triplets/s',
+            'n_gpus': world, 'steps': m['steps'], 'warmup': m['warm'], 'ms_per_step': m['ms_total'] / m['steps'],
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': CFG_WORKLOAD[args.cfg], 'global_batch': world * B, 'per_gpu_batch': B,
                        'frame': '%dx%d' % (H, W), 'levels': NLEVELS, 'parallelism': 'dp%d' % world,
-                       'conv_math': 'tcgen05 kind::tf32 x3 split precision (fp32-accurate, <=1e-4 parity)', 'cuda_graph': use_graph,
+                       'conv_math': 'tcgen05 kind::tf32 x3 split precision (fp32-accurate, <=1e-4 parity)', 'cuda_graph': m['use_graph'],
                        'numa_bound': numa_bound,
-                       'l2_policy': 'inputs and activations (~1 GB/step) exceed the 126 MB L2; no explicit flush',
+                       'l2_policy': 'inputs and activations (>1 GB/step) exceed the 126 MB L2; no explicit flush',
                        'e2e_input_path': ('pinned host batch -> H2D on a copy stream one step ahead (HostFeeder) -> D2D into the graph inputs; '
                                           'all steps+copies inside the timed region') if args.feed == 'prefetch' else
                                          'pinned host batch -> H2D into the graph inputs on the compute stream'},
-            'e2e': {'value': e2e, 'unit': 'triplets/s', 'h2d_bytes_per_step': in_bytes, 'd2h_bytes_per_step': 4,
-                    'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': int(launches_per_step * args.steps), 'gpu_launches_per_step': int(launches_per_step),
-            'clocks': clocks, 'loss': last_loss, 'peaks': pk,
+            'e2e': {'value': tps(m['ms_e2e'], m['steps']), 'unit': 'triplets/s', 'h2d_bytes_per_step': m['in_bytes'], 'd2h_bytes_per_step': 4,
+                    'ms_per_step': m['ms_e2e'] / m['steps']},
+            'gpu_launches': int(m['launches_per_step'] * m['steps']), 'gpu_launches_per_step': m['launches_per_step'],
+            'clocks': m['clocks'], 'loss': m['loss'], 'peaks': pk,
         }
-        out.update(prof.get('json', {}))
+        out.update(m['prof'].get('json', {}))
+        if side:
+            out['configs'] = {c: {'workload': CFG_WORKLOAD[c], 'value': tps(r['ms_total'], r['steps']), 'unit': 'triplets/s',
+                                  'ms_per_step': r['ms_total'] / r['steps'], 'steps': r['steps'],
+                                  'e2e': {'value': tps(r['ms_e2e'], r['steps']), 'ms_per_step': r['ms_e2e'] / r['steps'],
+                                          'h2d_bytes_per_step': r['in_bytes'], 'd2h_bytes_per_step': 4},
+                                  'gpu_launches_per_step': r['launches_per_step'], 'loss': r['loss']} for c, r in side.items()}
+        if ref_gpu is not None:
+            out['reference_gpu'] = ref_gpu
         if world == 1 and not args.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline(args.cfg, budget_s=25.0)
     return out
@@ -402,51 +434,121 @@ def pick_cpu_threads():
     return best, n
 
 
-def _oracle_step_timer(cfg, B, threads):
+def _ref_module():
+    p = os.path.join(ROOT, 'baseline')
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    import ref_step
+    return ref_step
+
+
+def _cpu_step_timer(cfg, B, threads):
+    """(run, kind, label): one reference train step on the host cores.  kind "reference" = the UNMODIFIED reference
+    modules under baseline/_ref driven by baseline/ref_step.py (stub correlation op); kind "port" = the oracle
+    restatement, only when baseline/_ref is absent."""
     from cc_b200 import synth
-    from oracle import step as OS
     torch.set_num_threads(threads)
-    P = OS.make_params(cfg)
-    opt = OS.Adam(OS.all_params(P), OS.HP['lr'], OS.HP['beta1'], OS.HP['beta2'])
     tgt, refs = synth.frames(B, H, W, seed=7)
     K, Kinv = synth.intrinsics(B, H, W)
+    rs = _ref_module()
+    if rs.available():
+        r = rs.Ref(cfg, 'cpu')
+
+        def run():
+            t0 = time.perf_counter()
+            r.step(tgt, refs, K, Kinv)
+            return time.perf_counter() - t0
+        return run, 'reference', 'unmodified reference modules (baseline/_ref), train.py:454-509,566-568 body, stub correlation op'
+    from oracle import step as OS
+    P = OS.make_params(cfg)
+    opt = OS.Adam(OS.all_params(P), OS.HP['lr'], OS.HP['beta1'], OS.HP['beta2'])
 
     def run():
         t0 = time.perf_counter()
         OS.train_step(cfg, P, opt, tgt, refs, K, Kinv)
         return time.perf_counter() - t0
-    return run
+    return run, 'port', 'oracle port of the reference step (baseline/_ref absent)'
 
 
 def cpu_baseline(cfg, budget_s=25.0):
-    """The oracle port of the reference step on the host cores, bounded to ~budget_s of CPU work."""
+    """The reference step on the host cores, bounded to ~budget_s of CPU work."""
     threads, ncores = pick_cpu_threads()
     B = 2
-    run = _oracle_step_timer(cfg, B, threads)
+    run, kind, label = _cpu_step_timer(cfg, B, threads)
     t_first = run()                      # warm-up (allocator, thread pool)
     ts = [run()]
     while sum(ts) + t_first + ts[-1] < budget_s and len(ts) < 5:
         ts.append(run())
     ts.sort()
     t = ts[len(ts) // 2]
-    return {'value': B / t, 'unit': 'triplets/s', 'cores': threads, 'kind': 'port',
-            'sample': '%s oracle step (fwd+bwd+Adam) at b%d 256x832x6lvl, torch CPU fp32, %d threads (fastest of a calibration sweep; box has %d cores), median of %d after 1 warm-up' % (cfg, B, threads, ncores, len(ts)),
+    return {'value': B / t, 'unit': 'triplets/s', 'cores': threads, 'kind': kind,
+            'sample': '%s step (fwd+bwd+Adam) at b%d 256x832x6lvl: %s; torch CPU fp32, %d threads (fastest of a calibration sweep; box has %d cores), median of %d after 1 warm-up' % (cfg, B, label, threads, ncores, len(ts)),
             's_per_step': t}
 
 
+def reference_gpu(cfg, dev, steps=5, warm=3):
+    """the reference PyTorch path itself on this B200 (cudnn.benchmark=True as train.py:299; TF32
+    on = the reference's default on this hardware, TF32 off = the parity setting), same batch shape.  Context for
+    the north-star's ">= 10x reference PyTorch on 1xB200"; not the denominator of the driver's ratio."""
+    from cc_b200 import synth
+    rs = _ref_module()
+    if not rs.available():
+        return {'unavailable': 'baseline/_ref missing'}
+    B = PER_GPU_BATCH
+    tgt, refs = synth.frames(B, H, W, seed=7)
+    K, Kinv = synth.intrinsics(B, H, W)
+    tgt, refs, K, Kinv = tgt.to(dev), [r.to(dev) for r in refs], K.to(dev), Kinv.to(dev)
+    saved = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    out = {'workload': CFG_WORKLOAD[cfg], 'per_gpu_batch': B, 'steps': steps, 'warmup': warm,
+           'note': 'unmodified reference modules (baseline/_ref) + pure-torch stub for the absent spatial_correlation_sampler; '
+                   'loss.item() every step as train.py:563'}
+    try:
+        for tf32 in (True, False):
+            torch.backends.cudnn.benchmark = True
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            r = rs.Ref(cfg, dev)
+            for _ in range(warm):
+                r.step(tgt, refs, K, Kinv).item()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                r.step(tgt, refs, K, Kinv).item()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out['tf32_on' if tf32 else 'tf32_off'] = {'ms_per_step': ms, 'value': B / (ms * 1e-3), 'unit': 'triplets/s'}
+            if not tf32:
+                try:                                            # kernel launches of one reference step
+                    from torch.profiler import profile, ProfilerActivity
+                    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                        r.step(tgt, refs, K, Kinv).item()
+                        torch.cuda.synchronize()
+                    out['gpu_launches_per_step'] = sum(int(e.count) for e in prof.key_averages() if e.device_type is not None and 'cuda' in str(e.device_type).lower())
+                except Exception as exc:
+                    out['gpu_launches_per_step'] = None
+                    out['launch_count_error'] = repr(exc)[:120]
+            del r
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    return out
+
+
 def run_reference(args):
-    """--impl reference: the reference algorithm's own CPU path (oracle port; the reference is pure Python/
-    PyTorch and cannot travel to the GPU box), all host threads, rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the step (unmodified modules under baseline/_ref,
+    driven by baseline/ref_step.py; oracle port only if that copy is absent), all the host threads it can use, rank 0 only."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return None
     threads, ncores = pick_cpu_threads()
     B = 2
-    run = _oracle_step_timer(args.cfg, B, threads)
+    run, kind, label = _cpu_step_timer(args.cfg, B, threads)
     probe = run()
     if probe * (args.steps + args.warmup) > 280 and B > 1:     # keep the whole run within a few minutes
         B = 1
-        run = _oracle_step_timer(args.cfg, B, threads)
+        run, kind, label = _cpu_step_timer(args.cfg, B, threads)
         run()
     for _ in range(max(0, args.warmup - 1)):
         run()
@@ -459,9 +561,9 @@ def run_reference(args):
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': CFG_WORKLOAD[args.cfg], 'sample_batch_per_step': B, 'frame': '%dx%d' % (H, W),
-                       'levels': NLEVELS, 'device': 'host CPU'},
-            'cpu_baseline': {'value': v, 'unit': 'triplets/s', 'cores': threads, 'kind': 'port',
-                             'sample': 'oracle %s step at b%d per step, %d steps, %d threads (fastest of a sweep; %d cores)' % (args.cfg, B, args.steps, threads, ncores)},
+                       'levels': NLEVELS, 'device': 'host CPU', 'reference_code': label},
+            'cpu_baseline': {'value': v, 'unit': 'triplets/s', 'cores': threads, 'kind': kind,
+                             'sample': '%s %s step at b%d per step, %d steps, %d threads (fastest of a sweep; %d cores)' % (label, args.cfg, B, args.steps, threads, ncores)},
             'e2e': {'value': v, 'unit': 'triplets/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
 
 
@@ -471,11 +573,13 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--cfg', default='cfg1', choices=sorted(CFG_WORKLOAD))
+    ap.add_argument('--cfg', default='cfg3', choices=sorted(CFG_WORKLOAD))
     ap.add_argument('--feed', default='prefetch', choices=['prefetch', 'inline'], help='e2e input path')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-side-configs', action='store_true', help='skip the cfg1/cfg2 side measurements (N=1)')
+    ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-PyTorch-on-this-GPU context run (N=1)')
     args = ap.parse_args()
     # Contract: rank 0 prints ONE JSON line on stdout.  Libraries chat on fd 1 (NCCL prints its version banner there):
     # park the real stdout, point fd 1 at stderr for the duration of the run, write the line to the real one at the end.

@@ -28,7 +28,9 @@ def build_nets(cfg, device, state_dicts=None, seed=0):
         elif name == 'mask':
             net = models.MaskNet6(nb_ref_imgs=4, output_exp=True)
         else:
-            net = models.Back2Future(nlevels=6)
+            # the five occlusion decoders are dead work in training: train.py:463 discards `occ` and they get no
+            # gradient; their parameters stay in the module (checkpoint contract) and in the optimiser
+            net = models.Back2Future(nlevels=6, compute_occ=False)
         net.init_weights()
         if state_dicts is not None and name in state_dicts:
             net.load_state_dict({k: v.clone() for k, v in state_dicts[name].items()}, strict=True)

@@ -153,9 +153,10 @@ def logical_or(a, b):
     return 1 - (1 - a) * (1 - b)
 
 
-def consensus_exp_masks(cam_flows_fwd, cam_flows_bwd, flows_fwd, flows_bwd, tgt_img, ref_img_fwd,
-                        ref_img_bwd, wssim, wrig, ws=0.1):
-    """0/1 targets, no grad.  Reference loss_functions.py:160-202."""
+def consensus_sides(cam_flows_fwd, cam_flows_bwd, flows_fwd, flows_bwd, tgt_img, ref_img_fwd,
+                    ref_img_bwd, wssim, wrig, ws=0.1):
+    """The two sides of the consensus comparison per level: (wrig * cam_err, flow_err).
+    Reference loss_functions.py:160-198 (the comparison itself is :199-200)."""
     def valid_of(w):
         return 1 - (w == 0).prod(1, keepdim=True).type_as(w)
 
@@ -173,8 +174,16 @@ def consensus_exp_masks(cam_flows_fwd, cam_flows_bwd, flows_fwd, flows_bwd, tgt_
         valid_cam = logical_or(valid_of(cam_f), valid_of(cam_b))
         cam_err = torch.min(err(tgt, cam_f), err(tgt, cam_b)) * valid_cam
         flow_err = err(tgt, flo_f)
-        out.append((wrig * cam_err <= (flow_err + epsilon)).type_as(cam_err))
+        out.append((wrig * cam_err, flow_err))
     return out
+
+
+def consensus_exp_masks(cam_flows_fwd, cam_flows_bwd, flows_fwd, flows_bwd, tgt_img, ref_img_fwd,
+                        ref_img_bwd, wssim, wrig, ws=0.1):
+    """0/1 targets, no grad.  Reference loss_functions.py:160-202."""
+    sides = consensus_sides(cam_flows_fwd, cam_flows_bwd, flows_fwd, flows_bwd, tgt_img, ref_img_fwd,
+                            ref_img_bwd, wssim, wrig, ws)
+    return [(lhs <= (rhs + epsilon)).type_as(lhs) for lhs, rhs in sides]
 
 
 def compute_joint_mask_for_depth(explainability_mask, rigidity_mask_bwd, rigidity_mask_fwd, THRESH):

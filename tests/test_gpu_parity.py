@@ -99,3 +99,10 @@ def test_conv_tma_family():
 
 def test_joint_step_cfg3_vs_oracle():
     SC.case_step_cfg3(torch.device('cuda:0'))
+
+
+def test_full_size_loss_layer_vs_cpu_oracle():
+    """The flow-photometric, smoothness, BCE and consensus kernels at the BASELINE size (b4 256x832, 6 levels: 960+
+    CTAs through the tile/prefix tables) against the CPU oracle."""
+    KC.case_loss_layer_fullsize(torch.device('cuda:0'), B=4, H=256, W=832, NL=6, oracle_device=torch.device('cpu'))
+    KC.case_consensus_fullsize(torch.device('cuda:0'), B=4, H=256, W=832, NL=6)

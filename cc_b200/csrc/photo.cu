@@ -35,6 +35,19 @@ __device__ __forceinline__ void locate_block(const PhotoArgs& a, int& l, int& b,
     x0 = (t % tx_n) * TW;
 }
 
+// depth_occlusion_masks of one pixel (loss_functions.py:132-137): the four rigid flows with the UNSCALED cameras
+// cams[0..3], pairs (0,3) and (1,2); returns (1 - occ) of the two pairs.  Not inlined: five call sites per thread
+// share one copy of the four projections (instruction-cache footprint of the fused kernel).
+__device__ __noinline__ float2 rigid_occ_pairs(const Cam* cams, float x, float y, float dep) {
+    float u[CCB_MAX_REFS], v[CCB_MAX_REFS];
+#pragma unroll
+    for (int i = 0; i < CCB_MAX_REFS; ++i) {
+        Proj pp = project(cams[i], x, y, dep, false);
+        coords_to_flow(cams[i], pp.Xn, pp.Yn, x, y, u[i], v[i]);
+    }
+    return make_float2(1.f - occ_mask(u[0], v[0], u[3], v[3]), 1.f - occ_mask(u[1], v[1], u[2], v[2]));
+}
+
 // ================================================================================================
 // Forward.  MODE: CCB_PHOTO_RIGID / FLOW / CONSENSUS.  SSIM=false compiles the 13x13 stage out.
 template <int MODE, bool SSIM>
@@ -47,9 +60,9 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
     float* sH = sy + 3 * T::PLANE;                    // [3][RH*HP]  (SSIM only)
     __shared__ Cam s_cam[2 * CCB_MAX_REFS];           // [i]: level-scaled cam of ref i; [R+i]: unscaled cam (occlusion)
     __shared__ float s_red[4 * 32];
-    __shared__ float s_g[CCB_SSIM_TAPS];
 
     const ccb_photo_desc& d = a.d;
+    const float* s_g = a.d.taps;                       // kernel-parameter (constant-bank) operands of the tap FMAs
     int l, b, x0, y0, local;
     locate_block(a, l, b, x0, y0, local);
     const int h = d.h[l], w = d.w[l], R = d.R;
@@ -57,7 +70,6 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
     const int tid = threadIdx.x;
     const int col = tid & 63, rg = tid >> 6;
     const float w1 = (float)(w - 1), h1 = (float)(h - 1);
-    if (tid < CCB_SSIM_TAPS) s_g[tid] = d.taps[tid];
     // ---- all cameras of this (level, batch) at once: threads 64.. build one each
     if (MODE == CCB_PHOTO_RIGID && tid >= 64 && tid < 64 + 2 * R) {
         const int k = tid - 64, i = (k < R) ? k : k - R;
@@ -77,10 +89,11 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
     }
     __syncthreads();
 
-    // ---- target moments, shared by all reference frames
+    // ---- target moments, shared by all reference frames.  The channel loops below stay LOOPS: fully unrolled the
+    // kernel was 12.6 k SASS instructions (200 KB) and 22 % of its stall samples were instruction fetch (ncu r01)
     float mu1[3][PXT], exx[3][PXT];
     if (SSIM) {
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 3; ++c) {
             hpass<0>(sx + c * Tile<6>::PLANE, nullptr, nullptr, sH, s_g);
             __syncthreads();
@@ -106,15 +119,9 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
         if (inimg[j] && d.has_occ && MODE != CCB_PHOTO_CONSENSUS) {
             const int off = py * w + px;
             if (MODE == CCB_PHOTO_RIGID) {
-                const float dep = __ldg(d.depth[l] + b * hw + off);
-                float u[CCB_MAX_REFS], v[CCB_MAX_REFS];
-#pragma unroll
-                for (int i = 0; i < CCB_MAX_REFS; ++i) {
-                    Proj pp = project(s_cam[R + i], (float)px, (float)py, dep, false);
-                    coords_to_flow(s_cam[R + i], pp.Xn, pp.Yn, (float)px, (float)py, u[i], v[i]);
-                }
-                om_pair[0][j] = 1.f - occ_mask(u[0], v[0], u[3], v[3]);
-                om_pair[1][j] = 1.f - occ_mask(u[1], v[1], u[2], v[2]);
+                const float2 om = rigid_occ_pairs(s_cam + R, (float)px, (float)py, __ldg(d.depth[l] + b * hw + off));
+                om_pair[0][j] = om.x;
+                om_pair[1][j] = om.y;
             } else {
                 const float* fb = d.flow[l][0] + b * 2 * hw + off;
                 const float* ff = d.flow[l][1] + b * 2 * hw + off;
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
         float gm[PXT], e_l1[PXT], e_ss[PXT];
 #pragma unroll
         for (int j = 0; j < PXT; ++j) { gm[j] = 0.f; e_l1[j] = 0.f; e_ss[j] = 0.f; }
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 3; ++c) {
             float o3[3][PXT];
             if (SSIM) {
@@ -296,9 +303,9 @@ __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(const PhotoArgs a) {
     float* sH = sD + 3 * T::PLANE;                    // [3][RH*HP]
     __shared__ Cam s_cam[CCB_MAX_REFS];
     __shared__ float s_red[12 * 32];
-    __shared__ float s_g[CCB_SSIM_TAPS];
 
     const ccb_photo_desc& d = a.d;
+    const float* s_g = a.d.taps;                       // constant-bank operands of the tap FMAs
     int l, b, x0, y0, local;
     locate_block(a, l, b, x0, y0, local);
     const int h = d.h[l], w = d.w[l], R = d.R;
@@ -306,7 +313,6 @@ __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(const PhotoArgs a) {
     const int tid = threadIdx.x;
     const int col = tid & 63, rg = tid >> 6;
     const float w1 = (float)(w - 1), h1 = (float)(h - 1);
-    if (tid < CCB_SSIM_TAPS) s_g[tid] = d.taps[tid];
     const float go = __ldg(d.grad_out);
     const float* tgt = d.tgt[l] + b * 3 * hw;
     if (MODE == CCB_PHOTO_RIGID && tid >= 64 && tid < 64 + R)
@@ -322,9 +328,11 @@ __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(const PhotoArgs a) {
         const float c_l = go * __ldg(d.scal + (l * R + i) * 4);
         const float c_s = c_l * d.wssim;
         // ---- blur the three dS maps of every channel
+        // channel and pixel loops are kept as loops (bl / gd live in local memory, L1-resident): unrolled, the kernel
+        // was 9.2 k SASS instructions and instruction fetch showed up as its top stall reason
         float bl[3][3][PXT];
         if (SSIM) {
-#pragma unroll
+#pragma unroll 1
             for (int c = 0; c < 3; ++c) {
                 const float* dm = d.dmaps[l] + ((b * R + i) * 9 + c * 3) * hw;
                 for (int idx = tid; idx < T::RH * T::RW; idx += NT) {
@@ -349,7 +357,7 @@ __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(const PhotoArgs a) {
         float acc[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) acc[k] = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < PXT; ++j) {
             int py = y0 + rg * PXT + j, px = x0 + col;
             if ((py < h) && (px < w)) {

@@ -36,31 +36,35 @@ __device__ __forceinline__ void hpass(const float* __restrict__ p0, const float*
     for (int k = 0; k < 20; ++k) a[k] = r0[k];
     float* o = sH + row * HP + cg * 8;
     constexpr int PL = T::RH * HP;
+    // products are formed once per staged value (20 per row segment), not once per (output, tap)
     if (KIND == 0) {
+        float aa[20];
+#pragma unroll
+        for (int k = 0; k < 20; ++k) aa[k] = a[k] * a[k];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
             for (int k = 0; k < 13; ++k) {
                 s0 = fmaf(g[k], a[j + k], s0);
-                s1 = fmaf(g[k], a[j + k] * a[j + k], s1);
+                s1 = fmaf(g[k], aa[j + k], s1);
             }
             o[j] = s0;
             o[PL + j] = s1;
         }
     } else if (KIND == 1) {
         const float* r1 = p1 + row * T::PITCH + cg * 8;
-        float b[20];
+        float b[20], bb[20], ab[20];
 #pragma unroll
-        for (int k = 0; k < 20; ++k) b[k] = r1[k];
+        for (int k = 0; k < 20; ++k) { b[k] = r1[k]; bb[k] = b[k] * b[k]; ab[k] = a[k] * b[k]; }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
             for (int k = 0; k < 13; ++k) {
                 s0 = fmaf(g[k], b[j + k], s0);
-                s1 = fmaf(g[k], b[j + k] * b[j + k], s1);
-                s2 = fmaf(g[k], a[j + k] * b[j + k], s2);
+                s1 = fmaf(g[k], bb[j + k], s1);
+                s2 = fmaf(g[k], ab[j + k], s2);
             }
             o[j] = s0;
             o[PL + j] = s1;

@@ -15,14 +15,20 @@ ACT = {None: _lib.ACT_NONE, 'none': _lib.ACT_NONE, 'relu': _lib.ACT_RELU, 'leaky
 CONV_IMPL = _lib.IMPL_AUTO          # tests flip this to force the FFMA or the tcgen05 path
 
 _WORK = {}
+_WORK_RETIRED = []          # outgrown buffers a captured CUDA graph may still point into: kept alive, never reused
+GRAPH_LIVE = False          # set by Trainer.capture(): from then on an outgrown workspace is retired, not freed
 
 
 def _workspace(dev, floats):
-    """One grow-only scratch buffer per device (split-K partials); stream-ordered reuse."""
+    """One grow-only scratch buffer per device (split-K partials, prepared weights); stream-ordered reuse.
+    The raw pointer is baked into captured CUDA graphs, so once a graph exists an outgrown buffer is parked in
+    _WORK_RETIRED instead of going back to the caching allocator (a replay would otherwise write into freed memory)."""
     if floats <= 0:
         return None, 0
     buf = _WORK.get(dev)
     if buf is None or buf.numel() < floats:
+        if buf is not None and GRAPH_LIVE:
+            _WORK_RETIRED.append(buf)
         buf = torch.empty(int(floats), device=dev, dtype=torch.float32)
         _WORK[dev] = buf
     return buf, buf.numel()
@@ -57,7 +63,18 @@ def _grad_slot(param, like):
     if slot is not None and not param._ccb_written:
         param._ccb_written = True
         return slot, True
+    if slot is not None:
+        param._ccb_indirect = True      # second use in one backward: this gradient reaches the flat buffer through AccumulateGrad
     return torch.empty_like(like), False
+
+
+def _grad_done(*params):
+    """Tell the data-parallel bucket scheduler (cc_b200.dist.GradBuckets) that the kernels writing these parameters'
+    gradients have been enqueued on the current stream."""
+    for p in params:
+        cb = getattr(p, '_ccb_bucket', None) if p is not None else None
+        if cb is not None:
+            cb.note(p)
 
 
 def _act_bwd(g, y, act, slope):
@@ -105,6 +122,7 @@ class _Conv2dFn(torch.autograd.Function):
             dw, w_direct = _grad_slot(ctx.params[0], w)
             db, b_direct = _grad_slot(ctx.params[1], w.new_empty(Co)) if has_bias else (None, False)
             _run(_lib.CONV_WGRAD, d, x, dz, dw, db)
+            _grad_done(ctx.params[0] if w_direct else None, ctx.params[1] if b_direct else None)
             dw = None if w_direct else dw
             db = None if b_direct else db
         return dx, dw, db, (dz if has_res else None), None, None, None, None
@@ -146,12 +164,14 @@ class _ConvT2dFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw, direct = _grad_slot(ctx.params[0], w)
             _run(_lib.CONV_WGRAD, d, dz, x, dw, None)        # roles swapped: activations = dz, grads = x
+            _grad_done(ctx.params[0] if direct else None)
             dw = None if direct else dw
         if has_bias and ctx.needs_input_grad[2]:
             db, direct = _grad_slot(ctx.params[1], w.new_empty(Cout))
             work, wf = _workspace(dz.device, _lib.lib().ccb_bias_grad_workspace_floats(B, Cout, H * W))
             _lib.check(_lib.lib().ccb_bias_grad(_lib.ptr(dz), _lib.ptr(db), B, Cout, H * W, _lib.ptr(work), wf, _lib.stream(dz)),
                        'bias_grad')
+            _grad_done(ctx.params[1] if direct else None)
             db = None if direct else db
         return dx, dw, db, None, None, None, None, None
 
@@ -185,6 +205,7 @@ class _BatchNormFn(torch.autograd.Function):
         work = torch.empty(_lib.lib().ccb_bn_workspace_floats(B, Cc, h * w), device=x.device)
         _lib.check(_lib.lib().ccb_bn_bwd(_lib.ptr(x), _lib.ptr(g), _lib.ptr(gamma), _lib.ptr(stats), _lib.ptr(dx),
                                          _lib.ptr(dg), _lib.ptr(db), B, Cc, h * w, _lib.ptr(work), _lib.stream(x)), 'bn_bwd')
+        _grad_done(ctx.params[0] if g_direct else None, ctx.params[1] if b_direct else None)
         return dx, (None if g_direct else dg), (None if b_direct else db), None, None, None, None, None
 
 

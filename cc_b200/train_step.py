@@ -101,37 +101,60 @@ class Trainer:
         params = [p for n in NETS_OF[cfg] for p in self.nets[n].parameters()]
         self.opt = FlatAdam(params, lr=hp['lr'], betas=(hp['beta1'], hp['beta2']))
         cdist.broadcast_params(self.opt)
+        self.buckets = cdist.GradBuckets(self.opt)          # overlapped gradient exchange (no-op at world size 1)
         self.graph = None
 
     def step(self, tgt, refs, K, Kinv):
         self.opt.zero_grad()
+        self.buckets.begin()
         loss, aux = LOSS_FNS[self.cfg](self.nets, tgt, refs, K, Kinv, self.hp)
         loss.backward()
-        cdist.allreduce_grads(self.opt)
+        self.buckets.finish()                               # waits for the bucket all-reduces issued during backward
         self.opt.step()
         return loss.detach(), aux
+
+    def _snapshot(self):
+        bufs = [b for n in self.nets.values() for b in n.buffers()]
+        return self.opt.snapshot(), [b.clone() for b in bufs]
+
+    def _restore(self, snap):
+        self.opt.restore(snap[0])
+        with torch.no_grad():
+            for b, s in zip([b for n in self.nets.values() for b in n.buffers()], snap[1]):
+                b.copy_(s)
 
     # ---- whole-step CUDA graph (static shapes): removes per-launch host latency --------------------
     def capture(self, tgt, refs, K, Kinv, warmup=2):
         """Capture zero_grad + forward + backward + all-reduce + Adam into one CUDA graph replaying on
         the static input buffers `tgt/refs/K/Kinv` (the caller copies each batch into them)."""
-        from . import pyramid
+        from . import pyramid, nn as cnn
         self.static_in = (tgt, refs, K, Kinv)
+        assert bool(torch.isfinite(tgt).all()), 'capture(): the static input buffers must hold a real batch'
+        # The warm-up runs real steps (allocator warm-up; bucket learning on the first one): they must not train.
+        # Parameters, Adam moments / step counter and BatchNorm buffers are restored afterwards.
+        snap = self._snapshot()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(warmup):
+            for _ in range(max(warmup, 2 if (self.buckets.enabled and self.buckets.buckets is None) else warmup)):
                 pyramid.clear()
                 self.step(tgt, refs, K, Kinv)
         torch.cuda.current_stream().wait_stream(s)
+        self._restore(snap)
         pyramid.clear()
+        cnn.GRAPH_LIVE = True                                # conv workspaces referenced by the graph are never freed
+        self._captured = dict(lr=self.opt.lr, grad_scale=self.opt.grad_scale)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_loss, _ = self.step(tgt, refs, K, Kinv)
+        self._restore(snap)                                  # capture itself does not execute, but keep the contract explicit
         pyramid.clear()
         return self.graph
 
     def replay(self):
+        # lr and grad_scale are kernel arguments baked into the graph: refuse to replay a stale one
+        assert self.opt.lr == self._captured['lr'] and self.opt.grad_scale == self._captured['grad_scale'], \
+            'learning rate / world size changed after capture(): re-capture the step'
         self.graph.replay()
         return self.static_loss
 

@@ -119,6 +119,11 @@ _SIGS = {
     'ccb_upsample2x_bwd': (_I, [_P, _P, _I, _I, _I, _P]),
     'ccb_adam_step': (_I, [_P, _P, _P, _P, _LL, _P, _F, _F, _F, _F, _F, _P]),
     'ccb_launch_count': (_LL, []),
+    'ccb_flow_metrics_workspace_bytes': (_LL, [_I, _I, _I]),
+    'ccb_flow_metrics': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P]),
+    'ccb_depth_errors_workspace_bytes': (_LL, [_I, _I, _I]),
+    'ccb_depth_errors': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    'ccb_prep_frames': (_I, [_P, C.POINTER(_P), _P, _P, _I, _I, _I, _I, _I, _I, _P]),
 }
 # entry points added by later translation units register themselves here (conv, nets, optimiser ...)
 EXTRA_SIGS = {}
@@ -164,12 +169,12 @@ def check(rc, what=''):
         raise RuntimeError('libccb200 %s failed (status %d): %s' % (what, rc, msg.decode() if msg else ''))
 
 
-def ptr(t, name='tensor'):
-    """Device pointer of a contiguous fp32 tensor (None -> NULL)."""
+def ptr(t, name='tensor', dtype=torch.float32):
+    """Device pointer of a contiguous tensor of `dtype` (fp32 unless stated; None -> NULL)."""
     if t is None:
         return None
-    if t.dtype != torch.float32:
-        raise TypeError('cc_b200: %s must be float32, got %s' % (name, t.dtype))
+    if t.dtype != dtype:
+        raise TypeError('cc_b200: %s must be %s, got %s' % (name, dtype, t.dtype))
     if not t.is_contiguous():
         raise ValueError('cc_b200: %s must be contiguous' % name)
     if not t.is_cuda and not is_simulator():

@@ -395,71 +395,59 @@ def weighted_binary_cross_entropy(output, target, weights=None):
 
 
 # ---- validation metrics (reference loss_functions.py:355-467; SURVEY 8f "next" N2) -----------------
-# Host-side torch reductions on eval outputs; kept so validate_*_with_gt (train.py:588-777) finds them.
-def _pred_at_gt_res(gt, pred):
-    """Bilinear-resize pred to gt's size and rescale the flow vectors to gt pixels."""
-    hp, wp = pred.shape[2], pred.shape[3]
-    hg, wg = gt.shape[2], gt.shape[3]
-    up = nn.functional.interpolate(pred, size=(hg, wg), mode='bilinear', align_corners=False)
-    return up[:, 0] * (wg / wp), up[:, 1] * (hg / hp)
+# Fused masked reductions (csrc/io_ops.cu): one pass over the ground-truth grid, deterministic two-stage sums,
+# no intermediate up-sampled tensors.  Same names / arguments / python-float results as the reference, so
+# validate_flow_with_gt / validate_depth_with_gt (train.py:588-777) call them unchanged.
+def _flow_metrics(gt, pred_a, pred_b=None, mask=None, thresh=0.5, tau=(3, 0.05), want_map=False):
+    gt, pred_a = _f(gt), _f(pred_a)
+    B, nc, Hg, Wg = gt.shape
+    hp, wp = int(pred_a.shape[2]), int(pred_a.shape[3])
+    hm = wm = 0
+    if mask is not None:
+        pred_b, mask = _f(pred_b), _f(mask)
+        assert pred_b.shape == pred_a.shape and mask.shape[1] == 1
+        hm, wm = int(mask.shape[2]), int(mask.shape[3])
+    lib = _lib.lib()
+    work = torch.empty(int(lib.ccb_flow_metrics_workspace_bytes(B, Hg, Wg) // 8) + 1, device=gt.device, dtype=torch.float64)
+    out = torch.empty(4, device=gt.device)
+    emap = torch.empty(B, Hg, Wg, device=gt.device) if want_map else None
+    _lib.check(lib.ccb_flow_metrics(_lib.ptr(gt, 'gt'), _lib.ptr(pred_a, 'pred'), _lib.ptr(pred_b), _lib.ptr(mask), B, int(nc),
+                                    int(Hg), int(Wg), hp, wp, hm, wm, float(thresh), float(tau[0]), float(tau[1]), _lib.ptr(emap),
+                                    _lib.ptr(work, 'work', torch.float64), _lib.ptr(out), _lib.stream(gt)), 'flow_metrics')
+    return out, emap
 
 
 def flow_diff(gt, pred):
     """Per-pixel end-point error map.  Reference loss_functions.py:355-365."""
-    u, v = _pred_at_gt_res(gt, pred)
-    return torch.sqrt((gt[:, 0] - u) ** 2 + (gt[:, 1] - v) ** 2)
+    return _flow_metrics(gt, pred, want_map=True)[1]
 
 
 def compute_epe(gt, pred):
     """Average EPE (masked by gt[:,2] when present) as a python float.  Reference :368-387."""
-    epe = flow_diff(gt, pred)
-    if gt.size(1) == 3:
-        valid = gt[:, 2]
-        avg = (epe * valid).sum() / (valid.sum() + epsilon)
-    else:
-        avg = epe.sum() / (gt.size(0) * gt.size(2) * gt.size(3))
-    return avg.item()
+    return _flow_metrics(gt, pred)[0][0].item()
 
 
 def outlier_err(gt, pred, tau=[3, 0.05]):
     """KITTI Fl outlier ratio.  Reference :389-407."""
-    valid = gt[:, 2]
-    epe = flow_diff(gt, pred) * valid
-    mag = torch.sqrt(gt[:, 0] ** 2 + gt[:, 1] ** 2)
-    bad = (epe > tau[0]).type_as(epe) * ((epe / (mag + epsilon)) > tau[1]).type_as(epe) * valid
-    return (bad.sum() / (valid.sum() + epsilon)).item()
+    assert gt.size(1) == 3
+    return _flow_metrics(gt, pred, tau=tau)[0][3].item()
 
 
 def compute_all_epes(gt, rigid_pred, non_rigid_pred, rigidity_mask, THRESH=0.5):
     """[all, rigid, non-rigid EPE, outliers] with the flows composited by the rigidity mask.  Reference :409-427."""
-    def resized(size):
-        return nn.functional.interpolate(rigidity_mask, size=size, mode='bilinear', align_corners=False)
-    m_pred, m_gt = resized(rigid_pred.shape[2:]), resized(gt.shape[2:])
-    non_rigid_pred = (m_pred <= THRESH).type_as(non_rigid_pred).expand_as(non_rigid_pred) * non_rigid_pred
-    rigid_pred = (m_pred > THRESH).type_as(rigid_pred).expand_as(rigid_pred) * rigid_pred
-    total = non_rigid_pred + rigid_pred
-    gt_non_rigid = (m_gt <= THRESH).type_as(gt).expand_as(gt) * gt
-    gt_rigid = (m_gt > THRESH).type_as(gt).expand_as(gt) * gt
-    return [compute_epe(gt, total), compute_epe(gt_rigid, rigid_pred), compute_epe(gt_non_rigid, non_rigid_pred),
-            outlier_err(gt, total)]
+    out = _flow_metrics(gt, rigid_pred, non_rigid_pred, rigidity_mask, thresh=THRESH)[0]
+    return out.tolist()
 
 
 def compute_errors(gt, pred, crop=True):
     """Depth metrics [abs_diff, abs_rel, sq_rel, a1, a2, a3] with median scaling and the Garg crop.
-    Reference :430-467."""
+    Reference :430-467 (returns 0-dim tensors like the reference; the per-sample medians are found by a
+    radix select on the device)."""
+    gt, pred = _f(gt), _f(pred)
     B, H, W = gt.shape
-    keep = torch.ones_like(gt[0], dtype=torch.bool)
-    if crop:
-        keep = torch.zeros_like(keep)
-        keep[int(0.40810811 * H):int(0.99189189 * H), int(0.03594771 * W):int(0.96405229 * W)] = True
-    sums = [0.0] * 6
-    for g, p in zip(gt, pred):
-        sel = (g > 0) & (g < 80) & keep
-        g, p = g[sel], p[sel].clamp(1e-3, 80)
-        p = p * torch.median(g) / torch.median(p)
-        ratio = torch.max(g / p, p / g)
-        err = (g - p).abs()
-        vals = [err.mean(), (err / g).mean(), (err ** 2 / g).mean()] + \
-               [(ratio < 1.25 ** k).float().mean() for k in (1, 2, 3)]
-        sums = [a + b for a, b in zip(sums, vals)]
-    return [v / B for v in sums]
+    lib = _lib.lib()
+    work = torch.empty(int(lib.ccb_depth_errors_workspace_bytes(B, H, W) // 8) + 1, device=gt.device, dtype=torch.float64)
+    out = torch.empty(6, device=gt.device)
+    _lib.check(lib.ccb_depth_errors(_lib.ptr(gt, 'gt'), _lib.ptr(pred, 'pred'), B, H, W, int(bool(crop)), _lib.ptr(work, 'work', torch.float64), _lib.ptr(out),
+                                    _lib.stream(gt)), 'depth_errors')
+    return [out[i] for i in range(6)]

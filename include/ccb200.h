@@ -277,6 +277,32 @@ int ccb_upsample2x_bwd(const float* dy, float* dx, int planes, int h, int w, ccb
 int ccb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                   float* state, float lr, float beta1, float beta2, float eps, float grad_scale,
                   ccb_stream_t stream);
+/* ---- callers either side of the step -------------------------------------------------------
+ * Validation metrics, reference loss_functions.py:355-467, as fused masked reductions (deterministic, no host sync).
+ * ccb_flow_metrics: gt [B,nc,Hg,Wg] (nc 3: third channel = valid mask; nc 2: plain mean), predictions [B,2,hp,wp]
+ *   bilinearly resized to the ground truth (F.upsample(size=gt) = align_corners False) and rescaled by Wg/wp, Hg/hp.
+ *   pred_nonrigid / rigidity_mask NULL: out4 = {compute_epe :368-387, -, -, outlier_err :389-407 with tau = (tau0, tau1)}.
+ *   Otherwise compute_all_epes :409-427 (mask [B,1,hm,wm], composite by mask > thresh at prediction resolution,
+ *   ground truth split at its own): out4 = {all, rigid, non-rigid EPE, outliers}.
+ *   epe_map (optional, [B,Hg,Wg]) receives flow_diff :355-365 of the (composited) prediction.
+ *   work: ccb_flow_metrics_workspace_bytes(B, Hg, Wg) bytes, 8-byte aligned.
+ * ccb_depth_errors: compute_errors :430-467 on gt, pred [B,H,W]: valid = 0 < gt < 80 (inside the Garg crop when
+ *   crop != 0), pred clamped to [1e-3, 80] and scaled by median(gt)/median(pred) per sample (lower medians, by radix
+ *   select on the device), out6 = batch means of {abs_diff, abs_rel, sq_rel, a1, a2, a3}. */
+long long ccb_flow_metrics_workspace_bytes(int B, int Hg, int Wg);
+int ccb_flow_metrics(const float* gt, const float* pred_rigid, const float* pred_nonrigid, const float* rigidity_mask,
+                     int B, int nc, int Hg, int Wg, int hp, int wp, int hm, int wm, float thresh, float tau0,
+                     float tau1, float* epe_map, void* work, float* out4, ccb_stream_t stream);
+long long ccb_depth_errors_workspace_bytes(int B, int H, int W);
+int ccb_depth_errors(const float* gt, const float* pred, int B, int H, int W, int crop, void* work, float* out6,
+                     ccb_stream_t stream);
+/* Input pipeline on the device (train.py:448-451 H2D + custom_transforms.py:21-30,47-118): uint8 HWC frames
+ * src [B,F,Hs,Ws,3] -> F normalised fp32 NCHW tensors dst[f] [B,3,H,W] = (v/255 - .5)/.5, per sample horizontally
+ * flipped (params[b][0] != 0) and scale-cropped: resized by (params[b][1], params[b][2]) = (scaled_w/Ws, scaled_h/Hs)
+ * with a half-pixel-centre bilinear lookup, then cropped at offs[b] = (x0, y0).  params [B,4] floats, offs [B,2] ints,
+ * device memory; dst = host array of F device pointers. */
+int ccb_prep_frames(const unsigned char* src_u8, float* const* dst, const float* params, const int* offs, int B, int F,
+                    int Hs, int Ws, int H, int W, ccb_stream_t stream);
 /* number of kernel launches issued through this library by the calling process so far */
 long long ccb_launch_count(void);
 

@@ -363,9 +363,79 @@ def gen_step(nets_):
     save('step_small', d)
 
 
+# --------------------------------------------------------------------------- F. validation metrics (N2)
+def gen_metrics():
+    """Reference loss_functions.py:355-467 on synthetic KITTI-like ground truth (sparse valid mask, odd sizes)."""
+    g = torch.Generator().manual_seed(70)
+    B, Hg, Wg, hp, wp, hm, wm = 2, 37, 122, 16, 52, 8, 26
+    gt = torch.cat((torch.randn(B, 2, Hg, Wg, generator=g) * 6, (torch.rand(B, 1, Hg, Wg, generator=g) > 0.6).float()), 1)
+    pr, pn = torch.randn(B, 2, hp, wp, generator=g) * 2, torch.randn(B, 2, hp, wp, generator=g) * 2
+    mask = torch.rand(B, 1, hm, wm, generator=g)
+    d = dict(gt=gt, pr=pr, pn=pn, mask=mask)
+    d['flow_diff'] = RL.flow_diff(gt, pr)
+    d['epe3'] = torch.tensor(RL.compute_epe(gt, pr))
+    d['epe2'] = torch.tensor(RL.compute_epe(gt[:, :2].contiguous(), pr))
+    d['outlier'] = torch.tensor(RL.outlier_err(gt, pr * 3))
+    d['all_epes'] = torch.tensor(RL.compute_all_epes(gt, pr, pn, mask))
+    d['all_epes_t3'] = torch.tensor(RL.compute_all_epes(gt, pr, pn, mask, THRESH=0.3))
+    Bd, H, W = 3, 48, 160
+    dgt = torch.rand(Bd, H, W, generator=g) * 100 - 10          # some <= 0 and >= 80: invalid
+    dpr = torch.rand(Bd, H, W, generator=g) * 60 + 0.5
+    dpr[0, :5] = 1e-5                                            # clamp path
+    d.update(dgt=dgt, dpr=dpr)
+    d['errors_crop'] = torch.stack([torch.as_tensor(v) for v in RL.compute_errors(dgt, dpr, crop=True)])
+    d['errors_nocrop'] = torch.stack([torch.as_tensor(v) for v in RL.compute_errors(dgt, dpr, crop=False)])
+    save('metrics_small', d)
+
+
+# --------------------------------------------------------------------------- G. input transforms (N1)
+def gen_transforms():
+    """The reference's train transform (custom_transforms.py, train.py:165-172) on uint8 frames.  scipy.misc (removed from
+    scipy) is stubbed with its historical implementation: imresize(arr, size) = PIL resize with BILINEAR (scipy 1.1
+    misc/pilutil.py)."""
+    import random as pyrandom
+    from PIL import Image
+    misc = types.ModuleType('scipy.misc')
+    misc.imresize = lambda arr, size: np.array(Image.fromarray(arr).resize((size[1], size[0]), resample=Image.BILINEAR))
+    misc.imrotate = lambda arr, angle: arr
+    sys.modules['scipy.misc'] = misc
+    import scipy
+    scipy.misc = misc
+    import custom_transforms as CT
+    rs = np.random.RandomState(5)
+    B, F, Hs, Ws = 3, 5, 32, 48
+    frames = rs.randint(0, 256, size=(B, F, Hs, Ws, 3)).astype(np.uint8)
+    K = np.array([[30.5, 0, 24.2], [0, 31.5, 15.1], [0, 0, 1]], np.float32)
+    tf = CT.Compose([CT.RandomHorizontalFlip(), CT.RandomScaleCrop(), CT.ArrayToTensor(), CT.Normalize(mean=[0.5, 0.5, 0.5], std=[0.5, 0.5, 0.5])])
+    pyrandom.seed(11)
+    np.random.seed(12)
+    outs, Ks = [], []
+    for b in range(B):
+        imgs, Kb = tf([frames[b, f] for f in range(F)], np.copy(K))
+        outs.append(torch.stack(imgs))
+        Ks.append(torch.from_numpy(np.asarray(Kb, np.float32)))
+    d = dict(frames=frames, K=K, out=torch.stack(outs), K_out=torch.stack(Ks), seed_random=11, seed_np=12)
+    # no-resize variant (flip + normalise only): must be reproduced exactly
+    tf2 = CT.Compose([CT.RandomHorizontalFlip(), CT.ArrayToTensor(), CT.Normalize(mean=[0.5, 0.5, 0.5], std=[0.5, 0.5, 0.5])])
+    pyrandom.seed(13)
+    outs2, K2 = [], []
+    for b in range(B):
+        imgs, Kb = tf2([frames[b, f] for f in range(F)], np.copy(K))
+        outs2.append(torch.stack(imgs))
+        K2.append(torch.from_numpy(np.asarray(Kb, np.float32)))
+    d.update(out_flip=torch.stack(outs2), K_flip=torch.stack(K2), seed_flip=13)
+    save('transforms_small', d)
+
+
 if __name__ == '__main__':
+    if 'extra' in sys.argv:                # only the round-2 fixtures (the round-1 files stay byte-identical)
+        gen_metrics()
+        gen_transforms()
+        sys.exit(0)
     gen_warp()
     gen_cfg0()
     gen_losses()
     ns = gen_nets()
     gen_step(ns)
+    gen_metrics()
+    gen_transforms()

@@ -106,3 +106,16 @@ def test_full_size_loss_layer_vs_cpu_oracle():
     CTAs through the tile/prefix tables) against the CPU oracle."""
     KC.case_loss_layer_fullsize(torch.device('cuda:0'), B=4, H=256, W=832, NL=6, oracle_device=torch.device('cpu'))
     KC.case_consensus_fullsize(torch.device('cuda:0'), B=4, H=256, W=832, NL=6)
+
+
+from tests import io_cases as IC   # noqa: E402
+
+
+@pytest.mark.parametrize('case', IC.IO_CASES, ids=lambda f: f.__name__)
+def test_io_case(case):
+    case(torch.device('cuda:0'))
+
+
+def test_io_full_size():
+    IC.case_metrics_oracle_sizes(torch.device('cuda:0'))
+    IC.case_input_pipeline_fullsize(torch.device('cuda:0'))

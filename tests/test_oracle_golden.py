@@ -236,3 +236,51 @@ def test_oracle_adam_matches_torch():
             (p.sin() * p).sum().backward()
             o.step()
     assert_close(a, b, 1e-6)
+
+
+def test_validation_metrics():
+    """oracle/metrics.py against the reference's loss_functions.py:355-467 (fixture frozen from the reference)."""
+    from oracle import metrics as OM
+    g = golden('metrics_small')
+    gt, pr, pn, mask = T(g['gt']), T(g['pr']), T(g['pn']), T(g['mask'])
+    assert_close(OM.flow_diff(gt, pr), g['flow_diff'], 1e-6)
+    assert abs(OM.compute_epe(gt, pr) - float(g['epe3'])) <= 1e-6 * float(g['epe3'])
+    assert abs(OM.compute_epe(gt[:, :2].contiguous(), pr) - float(g['epe2'])) <= 1e-6 * float(g['epe2'])
+    assert abs(OM.outlier_err(gt, pr * 3) - float(g['outlier'])) <= 1e-6
+    assert_close(torch.tensor(OM.compute_all_epes(gt, pr, pn, mask)), g['all_epes'], 1e-6)
+    assert_close(torch.tensor(OM.compute_all_epes(gt, pr, pn, mask, THRESH=0.3)), g['all_epes_t3'], 1e-6)
+    for crop, key in ((True, 'errors_crop'), (False, 'errors_nocrop')):
+        assert_close(torch.stack([torch.as_tensor(v) for v in OM.compute_errors(T(g['dgt']), T(g['dpr']), crop=crop)]), g[key], 1e-6)
+
+
+def _transform_params(g, key_random, seed_np, B, Hs, Ws, scale_crop):
+    import random
+    import numpy as np
+    from cc_b200.input_pipeline import draw_params
+    # the reference draws flip and scale/crop decisions sample by sample in Compose order: same generators, same order
+    random.seed(int(g[key_random]))
+    if seed_np is not None:
+        np.random.seed(int(seed_np))
+    return draw_params(B, Hs, Ws, scale_crop=scale_crop)
+
+
+def test_input_transforms():
+    """oracle/transforms.py (and the host-side parameter draw / intrinsics update of cc_b200.input_pipeline) against the
+    reference's Compose([RandomHorizontalFlip, RandomScaleCrop, ArrayToTensor, Normalize]) run on uint8 frames."""
+    import numpy as np
+    from oracle import transforms as OT
+    from cc_b200.input_pipeline import augment_intrinsics
+    g = golden('transforms_small')
+    frames, K = g['frames'], g['K']
+    B, F, Hs, Ws, _ = frames.shape
+    p = _transform_params(g, 'seed_random', g['seed_np'], B, Hs, Ws, True)
+    out, Kb = OT.apply(frames, K, p)
+    assert np.array_equal(Kb, g['K_out']), 'intrinsics after flip + scale-crop must match the reference bit for bit'
+    assert np.array_equal(augment_intrinsics(np.broadcast_to(K, (B, 3, 3)), p, Ws), g['K_out'])
+    assert p['flip'].sum() > 0 and (p['scaled_w'] > Ws).any()
+    # PIL rounds the resampled image to uint8 after each of its two passes: <= 1 step per pass, in (v/255-.5)/.5 units
+    assert np.abs(out - g['out']).max() <= 2 * (2 / 255) + 1e-6
+    assert np.abs(out - g['out']).mean() <= 0.6 * (2 / 255)
+    p2 = _transform_params(g, 'seed_flip', None, B, Hs, Ws, False)
+    out2, K2 = OT.apply(frames, K, p2)
+    assert np.array_equal(out2, g['out_flip']) and np.array_equal(K2, g['K_flip'])

@@ -45,3 +45,15 @@ from tests import step_cases as SC   # noqa: E402
 @pytest.mark.parametrize('case', SC.STEP_CASES_SIM, ids=lambda f: f.__name__)
 def test_step_case(case):
     case(torch.device('cpu'))
+
+
+from tests import io_cases as IC   # noqa: E402
+
+
+@pytest.mark.parametrize('case', IC.IO_CASES, ids=lambda f: f.__name__)
+def test_io_case(case):
+    case(torch.device('cpu'))
+
+
+def test_metrics_other_sizes():
+    IC.case_metrics_oracle_sizes(torch.device('cpu'), B=1, Hg=47, Wg=150, hp=32, wp=96)

@@ -145,6 +145,50 @@ def pose_vec2mat(vec, rotation_mode='euler'):
     return torch.cat([rot_mat, translation], dim=2)
 
 
+# ---- stand-alone geometry helpers of the reference module (inverse_warp.py:13-79).  Inside the training step these
+# are fused into the photometric / warp kernels (csrc/geom.cuh); the module-level functions exist so that code
+# importing them by name keeps working.  Plain device-side tensor ops, same arithmetic and shapes as the reference.
+pixel_coords = None
+
+
+def set_id_grid(depth):
+    """[1,3,H,W] grid of (x, y, 1) pixel coordinates, cached in the module like the reference (inverse_warp.py:13-20)."""
+    global pixel_coords
+    b, h, w = depth.size()
+    i_range = torch.arange(0, h, device=depth.device).view(1, h, 1).expand(1, h, w).type_as(depth)
+    j_range = torch.arange(0, w, device=depth.device).view(1, 1, w).expand(1, h, w).type_as(depth)
+    ones = torch.ones(1, h, w, device=depth.device).type_as(depth)
+    pixel_coords = torch.stack((j_range, i_range, ones), dim=1)
+    return pixel_coords
+
+
+def pixel2cam(depth, intrinsics_inv):
+    """depth [B,H,W], K^-1 [B,3,3] -> camera-frame points [B,3,H,W].  Reference inverse_warp.py:31-45."""
+    global pixel_coords
+    b, h, w = depth.size()
+    if (pixel_coords is None) or pixel_coords.size(2) != h or pixel_coords.size(3) != w or pixel_coords.device != depth.device:
+        set_id_grid(depth)
+    cur = pixel_coords[:, :, :h, :w].expand(b, 3, h, w).contiguous().view(b, 3, -1)
+    return intrinsics_inv.bmm(cur).view(b, 3, h, w) * depth.unsqueeze(1)
+
+
+def cam2pixel(cam_coords, proj_c2p_rot, proj_c2p_tr, padding_mode):
+    """Camera-frame points [B,3,H,W] -> normalised pixel coordinates [B,H,W,2]; 'zeros': out-of-range coordinates are
+    rewritten to 2 (no gradient through the rewrite).  Reference inverse_warp.py:48-79."""
+    b, _, h, w = cam_coords.size()
+    flat = cam_coords.view(b, 3, -1)
+    pcoords = proj_c2p_rot.bmm(flat) if proj_c2p_rot is not None else flat
+    if proj_c2p_tr is not None:
+        pcoords = pcoords + proj_c2p_tr
+    X, Y, Z = pcoords[:, 0], pcoords[:, 1], pcoords[:, 2].clamp(min=1e-3)
+    X_norm = 2 * (X / Z) / (w - 1) - 1
+    Y_norm = 2 * (Y / Z) / (h - 1) - 1
+    if padding_mode == 'zeros':
+        X_norm = torch.where(((X_norm > 1) | (X_norm < -1)).detach(), torch.full_like(X_norm, 2), X_norm)
+        Y_norm = torch.where(((Y_norm > 1) | (Y_norm < -1)).detach(), torch.full_like(Y_norm, 2), Y_norm)
+    return torch.stack([X_norm, Y_norm], dim=2).view(b, h, w, 2)
+
+
 def inverse_warp(img, depth, pose, intrinsics, intrinsics_inv, rotation_mode='euler', padding_mode='zeros'):
     """Inverse warp a source image to the target image plane.  Reference inverse_warp.py:250-283."""
     check_sizes(img, 'img', 'B3HW')

@@ -427,10 +427,41 @@ def gen_transforms():
     save('transforms_small', d)
 
 
+# --------------------------------------------------------------------------- H. helper exports (a17) + B2F tables
+def gen_helpers():
+    """The small functions the reference module exports next to the losses (loss_functions.py:13-25,132-158,204-219,
+    252-261,343-352) and the channel-permutation tables Back2Future builds (models/back2future.py:56-59)."""
+    B, H, W, NL = 2, 32, 48, 3
+    s = synth.sample(B, H, W, seed=33, nlevels=NL)
+    d = dict(B=B, H=H, W=W, NL=NL)
+    d['spatial_normalize'] = RL.spatial_normalize(s['depth'][0])
+    x = s['flow_fwd'][0]
+    d['robust_l1'] = RL.robust_l1(x)
+    d['robust_l1_q'] = RL.robust_l1(x, q=0.35, eps=1e-3)
+    d['robust_l1_per_pix'] = RL.robust_l1_per_pix(x)
+    ob, of = RL.occlusion_masks(s['flow_bwd'][0] * 3, s['flow_fwd'][0] * 3)
+    d['occ_bw'], d['occ_fw'] = ob, of
+    d['depth_occ'] = RL.depth_occlusion_masks(s['depth'][0], s['pose'], s['K'], s['Kinv'])
+    d['gauss_expl'] = RL.gaussian_explainability_loss(s['emask'])
+    d['logical_or'] = RL.logical_or(s['emask'][0][:, :2], s['emask'][0][:, 2:])
+    rig_f = [(a - b).abs() for a, b in zip(s['flow_fwd'], s['flow_bwd'])]
+    rig_b = [(a + b).abs() * 0.5 for a, b in zip(s['flow_fwd'], s['flow_bwd'])]
+    jm = RL.compute_joint_mask_for_depth(s['emask'], rig_b, rig_f, 0.5)
+    for i in range(NL):
+        d[f'joint{i}'] = jm[i]
+    tgt = (s['emask'][0] > 0.5).float()
+    d['wbce'] = RL.weighted_binary_cross_entropy(s['emask'][0], tgt, [0.3, 0.7])
+    d['wbce_none'] = RL.weighted_binary_cross_entropy(s['emask'][0], tgt)
+    m = RM.Back2Future(nlevels=6)
+    d['idx_fwd'], d['idx_bwd'] = m.idx_fwd.cpu(), m.idx_bwd.cpu()
+    save('helpers_small', d)
+
+
 if __name__ == '__main__':
     if 'extra' in sys.argv:                # only the round-2 fixtures (the round-1 files stay byte-identical)
         gen_metrics()
         gen_transforms()
+        gen_helpers()
         sys.exit(0)
     gen_warp()
     gen_cfg0()
@@ -439,3 +470,4 @@ if __name__ == '__main__':
     gen_step(ns)
     gen_metrics()
     gen_transforms()
+    gen_helpers()

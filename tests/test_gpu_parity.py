@@ -119,3 +119,11 @@ def test_io_case(case):
 def test_io_full_size():
     IC.case_metrics_oracle_sizes(torch.device('cuda:0'))
     IC.case_input_pipeline_fullsize(torch.device('cuda:0'))
+
+
+from tests import helper_cases as HC   # noqa: E402
+
+
+@pytest.mark.parametrize('case', HC.HELPER_CASES, ids=lambda f: f.__name__)
+def test_helper_case(case):
+    case(torch.device('cuda:0'))

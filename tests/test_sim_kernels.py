@@ -57,3 +57,11 @@ def test_io_case(case):
 
 def test_metrics_other_sizes():
     IC.case_metrics_oracle_sizes(torch.device('cpu'), B=1, Hg=47, Wg=150, hp=32, wp=96)
+
+
+from tests import helper_cases as HC   # noqa: E402
+
+
+@pytest.mark.parametrize('case', HC.HELPER_CASES, ids=lambda f: f.__name__)
+def test_helper_case(case):
+    case(torch.device('cpu'))

@@ -348,8 +348,9 @@ class _Corr81Fn(torch.autograd.Function):
         d1 = torch.empty_like(f1) if ctx.needs_input_grad[0] else None
         d2 = torch.empty_like(f2) if ctx.needs_input_grad[1] else None
         if d1 is not None or d2 is not None:
+            work = torch.empty(B * 81 * h * w, device=f1.device) if d2 is not None else None
             _lib.check(_lib.lib().ccb_corr81_bwd(_lib.ptr(f1), _lib.ptr(f2), _lib.ptr(g), _lib.ptr(d1), _lib.ptr(d2), B, Cc,
-                                                 h, w, ctx.rev, _lib.stream(f1)), 'corr81_bwd')
+                                                 h, w, ctx.rev, _lib.ptr(work), _lib.stream(f1)), 'corr81_bwd')
         return d1, d2, None
 
 

@@ -251,8 +251,9 @@ int ccb_debug_conv_plan(const ccb_conv_desc* d, int op, int py, int px, int* out
  * featwarp: Model.warp :287-321 = grid_sample(x, grid+flow, padding border, align_corners False). */
 int ccb_corr81_fwd(const float* f1, const float* f2, float* out, int B, int C, int h, int w, int reversed,
                    ccb_stream_t stream);
+/* work: B*81*h*w floats (the mirrored gradient planes), required when d_f2 != NULL */
 int ccb_corr81_bwd(const float* f1, const float* f2, const float* grad_out, float* d_f1, float* d_f2, int B,
-                   int C, int h, int w, int reversed, ccb_stream_t stream);
+                   int C, int h, int w, int reversed, float* work, ccb_stream_t stream);
 int ccb_featwarp_fwd(const float* x, const float* flow, int B, int C, int h, int w, float* out,
                      ccb_stream_t stream);
 /* d_x must be zero-filled by the caller (scatter-add); d_flow / d_x may be NULL */

@@ -108,7 +108,8 @@ _SIGS = {
     'ccb_debug_tc_swap_strides': (None, [_I]),
     'ccb_debug_tma_status': (_I, [C.POINTER(C.c_uint)]),
     'ccb_debug_conv_plan': (_I, [C.POINTER(ConvDesc), _I, _I, _I, C.POINTER(_I)]),
-    'ccb_corr81_fwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'ccb_corr81_fwd_workspace_floats': (_LL, [_I, _I, _I, _I]),
+    'ccb_corr81_fwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _LL, _P]),
     'ccb_corr81_bwd': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     'ccb_featwarp_fwd': (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     'ccb_featwarp_bwd': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),

@@ -41,18 +41,20 @@ class Model(nn.Module):
             setattr(self, 'decoder_bwd%d' % lvl, conv_dec_block(dec_in[lvl]))
         for lvl in range(6, 1, -1):
             setattr(self, 'decoder_occ%d' % lvl, conv_dec_block(354 if lvl == 6 else dec_in[lvl]))
+        # ImageNet statistics of normalize(): non-persistent buffers (no state_dict key, follow .cuda(); a tensor built
+        # from a Python list inside forward would be a pageable H2D copy, which a CUDA-graph capture refuses)
+        self.register_buffer('_norm_mean', torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1), persistent=False)
+        self.register_buffer('_norm_std', torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1), persistent=False)
 
     def init_weights(self):
         cnn.xavier_init_(self, bias_uniform=True)
 
     def normalize(self, ims):
         """Reference back2future.py:118-132 ([-1,1] frames -> ImageNet-normalised)."""
-        out = []
-        for im in ims:
-            mean = im.new_tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
-            std = im.new_tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
-            out.append((im * 0.5 + 0.5 - mean) / std)
-        return out
+        mean, std = self._norm_mean, self._norm_std
+        if mean.device != ims[0].device:                 # module moved by hand / parameters only: follow the frames
+            mean, std = mean.to(ims[0].device), std.to(ims[0].device)
+        return [(im * 0.5 + 0.5 - mean) / std for im in ims]
 
     def warp(self, x, flo):
         return cnn.feat_warp(x, flo)

@@ -334,8 +334,10 @@ class _Corr81Fn(torch.autograd.Function):
         f1, f2 = _c(f1), _c(f2)
         B, Cc, h, w = f1.shape
         out = torch.empty(B, 81, h, w, device=f1.device, dtype=torch.float32)
+        wf = _lib.lib().ccb_corr81_fwd_workspace_floats(B, Cc, h, w)
+        work = torch.empty(wf, device=f1.device, dtype=torch.float32) if wf else None
         _lib.check(_lib.lib().ccb_corr81_fwd(_lib.ptr(f1), _lib.ptr(f2), _lib.ptr(out), B, Cc, h, w, int(reversed_),
-                                             _lib.stream(f1)), 'corr81_fwd')
+                                             _lib.ptr(work), wf, _lib.stream(f1)), 'corr81_fwd')
         ctx.save_for_backward(f1, f2)
         ctx.rev = int(reversed_)
         return out

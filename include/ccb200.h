@@ -249,8 +249,11 @@ int ccb_debug_conv_plan(const ccb_conv_desc* d, int op, int py, int px, int* out
  * zero padded, divided by C) with the reference's channel permutation baked in (reversed=0: idx_fwd,
  * 1: idx_bwd, :56-59).  f1,f2 [B,C,h,w] -> out [B,81,h,w].   d_f1 / d_f2 may be NULL.
  * featwarp: Model.warp :287-321 = grid_sample(x, grid+flow, padding border, align_corners False). */
+/* work: ccb_corr81_fwd_workspace_floats() floats (per-channel-chunk partial sums; 0 when one CTA per tile sums all
+ * channels) */
+long long ccb_corr81_fwd_workspace_floats(int B, int C, int h, int w);
 int ccb_corr81_fwd(const float* f1, const float* f2, float* out, int B, int C, int h, int w, int reversed,
-                   ccb_stream_t stream);
+                   float* work, long long work_floats, ccb_stream_t stream);
 /* work: B*81*h*w floats (the mirrored gradient planes), required when d_f2 != NULL */
 int ccb_corr81_bwd(const float* f1, const float* f2, const float* grad_out, float* d_f1, float* d_f2, int B,
                    int C, int h, int w, int reversed, float* work, ccb_stream_t stream);

@@ -245,20 +245,35 @@ def case_bce_consensus(device):
         assert_close(gg, g[f'cdfm_g{i}'], TOL, f'cdfm grad{i}')
 
 
-def check_consensus_targets(got, ref, sides, what='consensus target'):
+def check_consensus_targets(got, ref, sides, what='consensus target', sides64=None):
     """0/1 targets must equal the reference's EXCEPT where the comparison `wrig*cam_err <= flow_err + 1e-8`
     (loss_functions.py:199-200) is a genuine tie: both sides are sums of 169-tap SSIM windows, so two correct fp32
     evaluations (separable vs 2-D window, CPU vs GPU) differ by a few 1e-7 relative and may land on either side.
-    Every mismatching pixel has to be such a near-tie (|lhs - rhs| <= 1e-5 * max(|lhs|, |rhs|, 1e-3)); there is no
-    allowance for a fraction of arbitrary mismatches.  Returns (mismatches, pixels)."""
+    Every mismatching pixel has to be such a near-tie; there is no allowance for a fraction of arbitrary mismatches.
+    The tie band is |lhs - rhs| <= 1e-5 * max(|lhs|, |rhs|, 1e-3), or - when `sides64` (the same formulas evaluated in
+    fp64 on the same fp32 inputs) is given - the MEASURED noise of the reference's own fp32 evaluation: a pixel whose
+    exact margin is below 4x the 99.99th percentile of |margin_fp32 - margin_fp64| of its level is decided by rounding
+    in the reference itself (SSIM's sigma^2 = E[x^2] - mu^2 cancellation amplifies 1e-7 to ~1e-4 in flat regions).
+    Returns (mismatches, pixels)."""
     n_mis = n_px = 0
     for i, (t, r, (lhs, rhs)) in enumerate(zip(got, ref, sides)):
         t, r, lhs, rhs = t.cpu(), r.cpu(), lhs.detach().cpu(), rhs.detach().cpu()
         assert set(torch.unique(t).tolist()) <= {0.0, 1.0}, f'{what} level {i}: not a 0/1 map'
         mis = t != r
         tie = (lhs - rhs).abs() <= 1e-5 * torch.maximum(torch.maximum(lhs.abs(), rhs.abs()), torch.tensor(1e-3))
+        note = ''
+        if sides64 is not None:
+            l64, r64 = sides64[i][0].detach().cpu(), sides64[i][1].detach().cpu()
+            m32, m64 = (lhs - rhs).double(), l64 - r64
+            noise = float(torch.quantile((m32 - m64).abs().flatten()[:: max(1, m32.numel() // 1000000)], 0.9999))
+            tie = tie | (m64.abs() <= 4 * noise)
+            note = ' (fp32-vs-fp64 reference noise p99.99 %.2e)' % noise
+            if int(mis.sum()):
+                idx = mis.nonzero()[:8]
+                print(f'{what} level {i}: {int(mis.sum())} flips{note}; exact margins of the first: ' +
+                      ', '.join('%.2e' % float(m64[tuple(j)]) for j in idx))
         bad = int((mis & ~tie).sum())
-        assert bad == 0, f'{what} level {i}: {bad} mismatching pixels that are not near-ties (of {int(mis.sum())} mismatches)'
+        assert bad == 0, f'{what} level {i}: {bad} mismatching pixels that are not near-ties (of {int(mis.sum())} mismatches){note}'
         n_mis += int(mis.sum())
         n_px += t.numel()
     return n_mis, n_px
@@ -275,7 +290,10 @@ def case_consensus_fullsize(device, B=4, H=256, W=832, NL=6, seed=31):
                                 wssim=0.997, wrig=1.0, ws=0.1)
     sides = OL.consensus_sides(cam_f, cam_b, ff, fb, s['tgt'], s['refs'][2], s['refs'][1], wssim=0.997, wrig=1.0)
     ref = [(lhs <= (rhs + 1e-8)).float() for lhs, rhs in sides]
-    n_mis, n_px = check_consensus_targets(tg, ref, sides)
+    d64 = lambda x: [t.double() for t in x] if isinstance(x, list) else x.double()
+    sides64 = OL.consensus_sides(d64(cam_f), d64(cam_b), d64(ff), d64(fb), d64(s['tgt']), d64(s['refs'][2]), d64(s['refs'][1]),
+                                 wssim=0.997, wrig=1.0)
+    n_mis, n_px = check_consensus_targets(tg, ref, sides, sides64=sides64)
     print('consensus targets b%d %dx%dx%d: %d near-tie flips of %d pixels' % (B, H, W, NL, n_mis, n_px))
     frac = sum(float(t.mean()) for t in tg) / NL
     assert 0.02 < frac < 0.98, 'degenerate consensus test (target fraction %.3f)' % frac

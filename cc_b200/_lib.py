@@ -61,7 +61,7 @@ class BceDesc(C.Structure):
 
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ('B', 'Ci', 'Hi', 'Wi', 'Co', 'Ho', 'Wo', 'kh', 'kw', 'stride', 'pad', 'act')] + \
-               [('slope', C.c_float), ('impl', C.c_int)]
+               [('slope', C.c_float), ('impl', C.c_int), ('wcache', C.c_void_p)]
 
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
@@ -103,11 +103,20 @@ _SIGS = {
     'ccb_conv2d_dgrad': (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _LL, _P]),
     'ccb_conv2d_wgrad': (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _LL, _P]),
     'ccb_act_bwd': (_I, [_P, _P, _P, _LL, _I, _F, _P]),
+    'ccb_act_bwd_bias_workspace_floats': (_LL, [_I, _I, _I]),
+    'ccb_act_bwd_bias': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _LL, _P]),
     'ccb_bias_grad_workspace_floats': (_LL, [_I, _I, _I]),
     'ccb_bias_grad': (_I, [_P, _P, _I, _I, _I, _P, _LL, _P]),
     'ccb_debug_tc_swap_strides': (None, [_I]),
     'ccb_debug_tma_status': (_I, [C.POINTER(C.c_uint)]),
     'ccb_debug_conv_plan': (_I, [C.POINTER(ConvDesc), _I, _I, _I, C.POINTER(_I)]),
+    'ccb_wcache_create': (C.c_void_p, []),
+    'ccb_wcache_destroy': (None, [C.c_void_p]),
+    'ccb_wcache_plan_floats': (_LL, [C.c_void_p]),
+    'ccb_wcache_table_bytes': (_LL, [C.c_void_p]),
+    'ccb_wcache_commit': (_I, [C.c_void_p, _P, _LL, _P, _LL, _P]),
+    'ccb_wcache_refresh': (_I, [C.c_void_p, _P]),
+    'ccb_wcache_stats': (None, [C.c_void_p, C.POINTER(C.c_longlong * 4)]),
     'ccb_corr81_fwd_workspace_floats': (_LL, [_I, _I, _I, _I]),
     'ccb_corr81_fwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _LL, _P]),
     'ccb_corr81_bwd': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),

@@ -47,6 +47,10 @@ struct WPrepDesc {
 };
 #ifndef CCB_CPU_SIM
 int launch_wprep(const WPrepDesc& d, cudaStream_t st);
+// prepared copy of d.w in d's layout: from the active weight cache (ccb_conv_desc.wcache) or produced now in d.wp
+int wprep_get(const WPrepDesc& d, cudaStream_t st, const float** out);
+struct WCache;
+extern thread_local WCache* g_cur_wcache;
 #endif
 
 // ---- small device helpers ----

@@ -300,6 +300,72 @@ __global__ void bias_grad_merge_kernel(const float* __restrict__ part, float* __
     db[c] = a;
 }
 
+// dz = dy * act'(y) and db[c] = sum_{b,px} dz in ONE pass over the gradient (act_bwd + bias_grad read it twice and cost
+// ~200 launches per step).  Large planes: grid (chunks, B, C), 256 threads x float4, per-CTA partial -> abb_merge_kernel;
+// small planes (B * plane <= ABB_SMALL): one CTA per channel does everything.  Fixed summation order.
+constexpr int ABB_CHUNK = 4096, ABB_SMALL = 8192;
+__device__ __forceinline__ float act_grad(float g, float yv, int act, float slope) {
+    switch (act) {
+        case CCB_ACT_RELU: return (yv > 0.f) ? g : 0.f;
+        case CCB_ACT_LEAKY: return (yv > 0.f) ? g : g * slope;
+        case CCB_ACT_SIGMOID: return g * yv * (1.f - yv);
+        default: return g;
+    }
+}
+__global__ void __launch_bounds__(256) abb_large_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
+                                                        float* __restrict__ part, int C, int plane, int nchunk, int act, float slope) {
+    __shared__ float s_red[32];
+    const int chunk = blockIdx.x, b = blockIdx.y, c = blockIdx.z;
+    const long long base = ((long long)b * C + c) * plane;
+    const int beg = chunk * ABB_CHUNK, end = min(plane, beg + ABB_CHUNK);
+    float v[1] = {0.f};
+    if ((plane & 3) == 0) {
+        for (int i = beg + threadIdx.x * 4; i < end; i += 1024) {
+            float4 g = __ldg((const float4*)(dy + base + i));
+            if (act != CCB_ACT_NONE) {
+                const float4 yv = __ldg((const float4*)(y + base + i));
+                g.x = act_grad(g.x, yv.x, act, slope); g.y = act_grad(g.y, yv.y, act, slope);
+                g.z = act_grad(g.z, yv.z, act, slope); g.w = act_grad(g.w, yv.w, act, slope);
+                *(float4*)(dz + base + i) = g;
+            }
+            v[0] += (g.x + g.y) + (g.z + g.w);
+        }
+    } else {
+        for (int i = beg + threadIdx.x; i < end; i += 256) {
+            float g = __ldg(dy + base + i);
+            if (act != CCB_ACT_NONE) { g = act_grad(g, __ldg(y + base + i), act, slope); dz[base + i] = g; }
+            v[0] += g;
+        }
+    }
+    if (part == nullptr) return;
+    block_sum<1>(v, s_red);
+    if (threadIdx.x == 0) part[((long long)c * gridDim.y + b) * nchunk + chunk] = v[0];
+}
+__global__ void __launch_bounds__(128) abb_merge_kernel(const float* __restrict__ part, float* __restrict__ db, int C, int n) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= C) return;
+    float a = 0.f;
+    for (int s = 0; s < n; ++s) a += part[(long long)c * n + s];
+    db[c] = a;
+}
+__global__ void __launch_bounds__(256) abb_small_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
+                                                        float* __restrict__ db, int B, int C, int plane, int act, float slope) {
+    __shared__ float s_red[32];
+    const int c = blockIdx.x;
+    float v[1] = {0.f};
+    for (int b = 0; b < B; ++b) {
+        const long long base = ((long long)b * C + c) * plane;
+        for (int i = threadIdx.x; i < plane; i += 256) {
+            float g = __ldg(dy + base + i);
+            if (act != CCB_ACT_NONE) { g = act_grad(g, __ldg(y + base + i), act, slope); dz[base + i] = g; }
+            v[0] += g;
+        }
+    }
+    if (db == nullptr) return;
+    block_sum<1>(v, s_red);
+    if (threadIdx.x == 0) db[c] = v[0];
+}
+
 static int launch_bias_grad(const float* dy, float* db, int B, int C, int plane, float* work, long long work_floats,
                             cudaStream_t st) {
     const long long per = (long long)B * plane;
@@ -409,6 +475,16 @@ static bool use_tma(const ccb_conv_desc* d, int op, const void* src) {
     return true;
 }
 
+// the weight cache of the conv call in flight (wprep_get looks it up); sim builds have none
+struct WCacheScope {
+#ifndef CCB_CPU_SIM
+    explicit WCacheScope(void* h) { g_cur_wcache = (WCache*)h; }
+    ~WCacheScope() { g_cur_wcache = nullptr; }
+#else
+    explicit WCacheScope(void*) {}
+#endif
+};
+
 // 0: FFMA, 1: tcgen05 3xTF32, 2: tcgen05 single TF32
 static int pick_impl(const ccb_conv_desc* d, int op) {
     switch (d->impl) {
@@ -490,6 +566,7 @@ extern "C" int ccb_conv2d_fprop(const ccb_conv_desc* d, const float* x, const fl
     int rc = fill_conv(a, d);
     if (rc) return rc;
     CCB_REQUIRE(x && w && y, CCB_ERR_ARG, "conv2d_fprop: null pointer");
+    WCacheScope wc_scope(d->wcache);
     {
         int impl = pick_impl(d, CCB_CONV_FPROP);
         CCB_REQUIRE(impl >= 0, CCB_ERR_UNSUPPORTED, "conv2d_fprop: shape not supported by the tensor-core path");
@@ -509,6 +586,7 @@ extern "C" int ccb_conv2d_dgrad(const ccb_conv_desc* d, const float* dy, const f
     int rc = fill_conv(a, d);
     if (rc) return rc;
     CCB_REQUIRE(dy && w && dx, CCB_ERR_ARG, "conv2d_dgrad: null pointer");
+    WCacheScope wc_scope(d->wcache);
     {
         int impl = pick_impl(d, CCB_CONV_DGRAD);
         CCB_REQUIRE(impl >= 0, CCB_ERR_UNSUPPORTED, "conv2d_dgrad: shape not supported by the tensor-core path");
@@ -597,6 +675,28 @@ extern "C" int ccb_act_bwd(const float* dy, const float* y, float* dz, long long
     if (numel == 0) return CCB_OK;
     CCB_LAUNCH(act_bwd_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), 0, stream, dy, y, dz, numel, act, slope);
     return check_launch("act_bwd");
+}
+
+extern "C" long long ccb_act_bwd_bias_workspace_floats(int B, int C, int plane) {
+    if ((long long)B * plane <= ABB_SMALL) return 0;
+    return (long long)C * B * cdiv(plane, ABB_CHUNK);
+}
+// dz = dy * act'(y) (skipped, dz untouched, when act == NONE) and, when db != NULL, db[c] = sum over (b, pixel) of dz.
+extern "C" int ccb_act_bwd_bias(const float* dy, const float* y, float* dz, float* db, int B, int C, int plane, int act, float slope,
+                                float* work, long long work_floats, ccb_stream_t stream) {
+    CCB_REQUIRE(dy && B >= 1 && C >= 1 && plane >= 1, CCB_ERR_ARG, "act_bwd_bias: bad argument");
+    CCB_REQUIRE(act == CCB_ACT_NONE || (y && dz), CCB_ERR_ARG, "act_bwd_bias: y and dz required with an activation");
+    if (act == CCB_ACT_NONE && db == nullptr) return CCB_OK;
+    if ((long long)B * plane <= ABB_SMALL) {
+        CCB_LAUNCH(abb_small_kernel, dim3(C), dim3(256), 0, stream, dy, y, dz, db, B, C, plane, act, slope);
+        return check_launch("act_bwd_bias");
+    }
+    const int nchunk = cdiv(plane, ABB_CHUNK);
+    CCB_REQUIRE(db == nullptr || (work && work_floats >= (long long)C * B * nchunk), CCB_ERR_ARG, "act_bwd_bias: workspace too small");
+    CCB_REQUIRE(C <= 65535 && B <= 65535, CCB_ERR_ARG, "act_bwd_bias: grid too large");
+    CCB_LAUNCH(abb_large_kernel, dim3(nchunk, B, C), dim3(256), 0, stream, dy, y, dz, db ? work : nullptr, C, plane, nchunk, act, slope);
+    if (db) CCB_LAUNCH(abb_merge_kernel, dim3(cdiv(C, 128)), dim3(128), 0, stream, (const float*)work, db, C, B * nchunk);
+    return check_launch("act_bwd_bias");
 }
 
 extern "C" long long ccb_bias_grad_workspace_floats(int B, int C, int plane) {

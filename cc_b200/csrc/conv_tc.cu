@@ -418,9 +418,10 @@ static int launch_tc(TcArgs& a, const float* w, int mode, int N, int Cc, int KK,
     p.w = w; p.wp = work; p.N = N; p.Cc = Cc; p.KK = KK; p.ntaps = a.ntaps; p.Kp = a.Kp; p.mode = mode; p.Ci = Ci;
     p.layout = WPREP_TC; p.p0 = a.cpad;
     for (int t = 0; t < a.ntaps; ++t) p.tap_index[t] = tap_index[t];
-    int rc = launch_wprep(p, st);
+    const float* wpp = nullptr;
+    int rc = wprep_get(p, st, &wpp);
     if (rc) return rc;
-    a.wp = work;
+    a.wp = wpp;
     a.Ntot = N;
     a.splits = splits;
     a.kt_per_split = cdiv(a.Kp / (TC_KC * 4), splits);

@@ -425,7 +425,8 @@ static int launch_tma(const float* x, int B, int Cc, int Hin, int Win, const flo
     CCB_REQUIRE(wp_floats <= work_floats, CCB_ERR_ARG, "conv_tma: workspace too small");
     p.w = w; p.wp = work; p.N = N; p.Cc = Cc; p.KK = KK; p.Ci = Ci; p.mode = mode; p.Kp = Kp; p.ntaps = ntaps;
     p.layout = WPREP_TMA; p.p0 = a.cb; p.p1 = a.cblocks; p.p2 = a.units;
-    int rc = launch_wprep(p, st);
+    const float* wpp = nullptr;
+    int rc = wprep_get(p, st, &wpp);
     if (rc) return rc;
     const int ntile_max = N < 128 ? N : 128;
     int nalloc = 16;
@@ -453,7 +454,7 @@ static int launch_tma(const float* x, int B, int Cc, int Hin, int Win, const flo
         cuuint64_t strides[1] = {(cuuint64_t)Kp * 4};
         cuuint32_t box[2] = {32, (cuuint32_t)nalloc};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)work, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wpp, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         CCB_REQUIRE(r == CUDA_SUCCESS, CCB_ERR_LAUNCH, "conv_tma: cuTensorMapEncodeTiled(B) failed (%d)", (int)r);
     }
@@ -909,7 +910,8 @@ static int launch_slab(const float* x, int B, int Cc, int Hin, int Win, const fl
     CCB_REQUIRE(2ll * N * Kp <= wp_floats, CCB_ERR_ARG, "conv_slab: workspace too small");
     pa.w = w; pa.wp = work; pa.N = N; pa.Cc = Cc; pa.KK = KK; pa.Ci = Ci; pa.mode = mode; pa.Kp = Kp; pa.ntaps = ntaps;
     pa.layout = WPREP_SLAB; pa.p0 = p.cs; pa.p1 = p.cblocks; pa.p2 = p.kt_full;
-    int rc = launch_wprep(pa, st);
+    const float* wpp = nullptr;
+    int rc = wprep_get(pa, st, &wpp);
     if (rc) return rc;
     alignas(64) CUtensorMap map_x, map_b;
     {
@@ -926,7 +928,7 @@ static int launch_slab(const float* x, int B, int Cc, int Hin, int Win, const fl
         cuuint64_t strides[1] = {(cuuint64_t)Kp * 4};
         cuuint32_t box[2] = {32, (cuuint32_t)p.nbox};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)work, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wpp, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         CCB_REQUIRE(r == CUDA_SUCCESS, CCB_ERR_LAUNCH, "conv_slab: cuTensorMapEncodeTiled(w) failed (%d)", (int)r);
     }

@@ -34,11 +34,53 @@ def _workspace(dev, floats):
     return buf, buf.numel()
 
 
+WCACHE = None               # handle of the weight cache conv calls use (set by Trainer.step for its own nets only)
+
+
+class WeightCache:
+    """Prepared (tf32 hi|lo, kernel K order) copies of the conv weights, refreshed once per optimiser step in ONE launch
+    instead of once per conv call (include/ccb200.h: ccb_wcache_*).  The first step run with the cache active RECORDS
+    the layouts; commit() allocates the persistent buffer; from then on conv calls skip their preparation launch.
+    Owner contract: refresh() after every change of the weights."""
+
+    def __init__(self, device):
+        self.device = device
+        self.h = _lib.lib().ccb_wcache_create()
+        self.committed = False
+        self.buf = self.table = None
+
+    def commit(self):
+        lib = _lib.lib()
+        floats, tbytes = lib.ccb_wcache_plan_floats(self.h), lib.ccb_wcache_table_bytes(self.h)
+        self.buf = torch.empty(max(int(floats), 1), device=self.device, dtype=torch.float32)
+        self.table = torch.empty(int(tbytes), device=self.device, dtype=torch.uint8)
+        _lib.check(lib.ccb_wcache_commit(self.h, self.buf.data_ptr(), floats, self.table.data_ptr(), tbytes,
+                                         torch.cuda.current_stream(self.device).cuda_stream), 'wcache_commit')
+        self.committed = True
+        self.refresh()
+
+    def refresh(self):
+        if self.committed:
+            _lib.check(_lib.lib().ccb_wcache_refresh(self.h, torch.cuda.current_stream(self.device).cuda_stream), 'wcache_refresh')
+
+    def stats(self):
+        out = (C.c_longlong * 4)()
+        _lib.lib().ccb_wcache_stats(self.h, C.byref(out))
+        return dict(layouts=out[0], hits=out[1], misses=out[2], committed=bool(out[3]))
+
+    def __del__(self):
+        try:
+            _lib.lib().ccb_wcache_destroy(self.h)
+        except Exception:
+            pass
+
+
 def _desc(B, Ci, Hi, Wi, Co, Ho, Wo, k, stride, pad, act, slope):
     d = _lib.ConvDesc()
     d.B, d.Ci, d.Hi, d.Wi, d.Co, d.Ho, d.Wo = B, Ci, Hi, Wi, Co, Ho, Wo
     d.kh = d.kw = k
     d.stride, d.pad, d.act, d.slope, d.impl = stride, pad, act, slope, CONV_IMPL
+    d.wcache = WCACHE
     return d
 
 
@@ -86,6 +128,21 @@ def _act_bwd(g, y, act, slope):
     return dz
 
 
+def _act_bwd_bias(g, y, act, slope, db):
+    """dz = g * act'(y) and (db given) db[c] = sum dz, one pass (ccb_act_bwd_bias)."""
+    if act == _lib.ACT_NONE and db is None:
+        return g
+    B, Cc = g.shape[0], g.shape[1]
+    plane = g.numel() // (B * Cc)
+    dz = torch.empty_like(g) if act != _lib.ACT_NONE else g
+    lib = _lib.lib()
+    wf = lib.ccb_act_bwd_bias_workspace_floats(B, Cc, plane) if db is not None else 0
+    work = torch.empty(wf, device=g.device, dtype=torch.float32) if wf else None
+    _lib.check(lib.ccb_act_bwd_bias(_lib.ptr(g), _lib.ptr(y), _lib.ptr(dz) if act != _lib.ACT_NONE else None, _lib.ptr(db),
+                                    B, Cc, plane, act, slope, _lib.ptr(work), wf, _lib.stream(g)), 'act_bwd_bias')
+    return dz
+
+
 class _Conv2dFn(torch.autograd.Function):
     """y = act(conv2d(x, w) + bias + res)"""
 
@@ -112,16 +169,17 @@ class _Conv2dFn(torch.autograd.Function):
         stride, pad, act, slope, has_bias, has_res = ctx.cfg
         B, Ci, Hi, Wi = x.shape
         Co, _, k, _ = w.shape
-        dz = _act_bwd(_c(g), y, act, slope)
+        want_w = ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])
+        db, b_direct = _grad_slot(ctx.params[1], w.new_empty(Co)) if (has_bias and want_w) else (None, False)
+        dz = _act_bwd_bias(_c(g), y, act, slope, db)          # activation backward + bias gradient: one pass over g
         d = _desc(B, Ci, Hi, Wi, Co, dz.shape[2], dz.shape[3], k, stride, pad, _lib.ACT_NONE, 0.0)
-        dx = dw = db = None
+        dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             _run(_lib.CONV_DGRAD, d, dz, w, None, None, dx)
-        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+        if want_w:
             dw, w_direct = _grad_slot(ctx.params[0], w)
-            db, b_direct = _grad_slot(ctx.params[1], w.new_empty(Co)) if has_bias else (None, False)
-            _run(_lib.CONV_WGRAD, d, x, dz, dw, db)
+            _run(_lib.CONV_WGRAD, d, x, dz, dw, None)
             _grad_done(ctx.params[0] if w_direct else None, ctx.params[1] if b_direct else None)
             dw = None if w_direct else dw
             db = None if b_direct else db
@@ -155,9 +213,14 @@ class _ConvT2dFn(torch.autograd.Function):
         stride, pad, act, slope, has_bias, H, W = ctx.cfg
         B, Cin, h, wd = x.shape
         _, Cout, k, _ = w.shape
-        dz = _act_bwd(_c(g), y, act, slope)
+        want_b = has_bias and ctx.needs_input_grad[2]
+        db, b_direct = _grad_slot(ctx.params[1], w.new_empty(Cout)) if want_b else (None, False)
+        dz = _act_bwd_bias(_c(g), y, act, slope, db)
+        if want_b:
+            _grad_done(ctx.params[1] if b_direct else None)
+            db = None if b_direct else db
         d = _desc(B, Cout, H, W, Cin, h, wd, k, stride, pad, _lib.ACT_NONE, 0.0)
-        dx = dw = db = None
+        dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             _run(_lib.CONV_FPROP, d, dz, w, None, None, dx)
@@ -166,13 +229,6 @@ class _ConvT2dFn(torch.autograd.Function):
             _run(_lib.CONV_WGRAD, d, dz, x, dw, None)        # roles swapped: activations = dz, grads = x
             _grad_done(ctx.params[0] if direct else None)
             dw = None if direct else dw
-        if has_bias and ctx.needs_input_grad[2]:
-            db, direct = _grad_slot(ctx.params[1], w.new_empty(Cout))
-            work, wf = _workspace(dz.device, _lib.lib().ccb_bias_grad_workspace_floats(B, Cout, H * W))
-            _lib.check(_lib.lib().ccb_bias_grad(_lib.ptr(dz), _lib.ptr(db), B, Cout, H * W, _lib.ptr(work), wf, _lib.stream(dz)),
-                       'bias_grad')
-            _grad_done(ctx.params[1] if direct else None)
-            db = None if direct else db
         return dx, dw, db, None, None, None, None, None
 
 

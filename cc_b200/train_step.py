@@ -103,14 +103,32 @@ class Trainer:
         cdist.broadcast_params(self.opt)
         self.buckets = cdist.GradBuckets(self.opt)          # overlapped gradient exchange (no-op at world size 1)
         self.graph = None
+        # prepared conv weights are refreshed once per optimiser step (one launch), not once per conv call
+        from . import nn as cnn, _lib
+        self.wcache = None if (_lib.is_simulator() or torch.device(device).type != 'cuda') else cnn.WeightCache(torch.device(device))
+
+    def refresh_weights(self):
+        """Call after changing parameters behind the trainer's back (load_state_dict, manual edits)."""
+        if self.wcache is not None:
+            self.wcache.refresh()
 
     def step(self, tgt, refs, K, Kinv):
+        from . import nn as cnn
         self.opt.zero_grad()
         self.buckets.begin()
-        loss, aux = LOSS_FNS[self.cfg](self.nets, tgt, refs, K, Kinv, self.hp)
-        loss.backward()
+        cnn.WCACHE = self.wcache.h if self.wcache is not None else None
+        try:
+            loss, aux = LOSS_FNS[self.cfg](self.nets, tgt, refs, K, Kinv, self.hp)
+            loss.backward()
+        finally:
+            cnn.WCACHE = None
         self.buckets.finish()                               # waits for the bucket all-reduces issued during backward
         self.opt.step()
+        if self.wcache is not None:
+            if not self.wcache.committed:
+                self.wcache.commit()                        # first step recorded the layouts: allocate + prepare
+            else:
+                self.wcache.refresh()
         return loss.detach(), aux
 
     def _snapshot(self):
@@ -122,6 +140,7 @@ class Trainer:
         with torch.no_grad():
             for b, s in zip([b for n in self.nets.values() for b in n.buffers()], snap[1]):
                 b.copy_(s)
+        self.refresh_weights()
 
     # ---- whole-step CUDA graph (static shapes): removes per-launch host latency --------------------
     def capture(self, tgt, refs, K, Kinv, warmup=2):
@@ -136,7 +155,10 @@ class Trainer:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(max(warmup, 2 if (self.buckets.enabled and self.buckets.buckets is None) else warmup)):
+            need = 2 if (self.buckets.enabled and self.buckets.buckets is None) else 0
+            if self.wcache is not None and not self.wcache.committed:
+                need = max(need, 1)                     # the weight cache records its layouts in an eager step
+            for _ in range(max(warmup, need)):
                 pyramid.clear()
                 self.step(tgt, refs, K, Kinv)
         torch.cuda.current_stream().wait_stream(s)

@@ -213,7 +213,23 @@ typedef struct ccb_conv_desc {
     int act;                /* CCB_ACT_* fused into the epilogue */
     float slope;            /* LeakyReLU negative slope */
     int impl;               /* CCB_CONV_IMPL_* */
+    void* wcache;           /* weight cache handle (ccb_wcache_create) or NULL: prepared weight copies are then made per call */
 } ccb_conv_desc;
+/* Weight cache.  The tensor-core kernels read weights from a prepared copy (tf32 hi | lo split, K order of the kernel).
+ * Without a cache every conv call prepares its copy into `work`.  With one (a trainer owns it; the weights then only
+ * change in the optimiser step): while the cache is RECORDING, conv calls note which prepared layouts they need (and still
+ * prepare on the spot); ccb_wcache_plan_floats / ccb_wcache_table_bytes size the caller-allocated persistent buffer and
+ * device table, ccb_wcache_commit binds them, ccb_wcache_refresh re-prepares EVERY copy in one launch (call it after each
+ * weight update), and conv calls whose (weights, layout) are recorded skip their preparation launch.
+ * The caller must refresh after ANY change of the weights (optimizer step, load_state_dict). */
+void* ccb_wcache_create(void);
+void ccb_wcache_destroy(void* cache);
+long long ccb_wcache_plan_floats(void* cache);
+long long ccb_wcache_table_bytes(void* cache);
+int ccb_wcache_commit(void* cache, float* buf, long long buf_floats, void* table, long long table_bytes, ccb_stream_t stream);
+int ccb_wcache_refresh(void* cache, ccb_stream_t stream);
+/* out4 = {recorded layouts, cache hits, misses after commit, state (0 recording, 1 committed)} */
+void ccb_wcache_stats(void* cache, long long* out4);
 long long ccb_conv_workspace_floats(const ccb_conv_desc* d, int op);
 int ccb_conv2d_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float* bias,
                      const float* res, float* y, float* work, long long work_floats, ccb_stream_t stream);
@@ -224,6 +240,11 @@ int ccb_conv2d_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, fl
 /* dz = dy * act'(.) expressed through the activation OUTPUT y (in place allowed: dz == dy). */
 int ccb_act_bwd(const float* dy, const float* y, float* dz, long long numel, int act, float slope,
                 ccb_stream_t stream);
+/* fused: dz = dy * act'(y) (not touched when act == CCB_ACT_NONE; in place allowed) and, when db != NULL,
+ * db[c] = sum over (b, pixel) of dz - one pass over the gradient.  work: ccb_act_bwd_bias_workspace_floats() floats. */
+long long ccb_act_bwd_bias_workspace_floats(int B, int C, int plane);
+int ccb_act_bwd_bias(const float* dy, const float* y, float* dz, float* db, int B, int C, int plane, int act, float slope,
+                     float* work, long long work_floats, ccb_stream_t stream);
 /* db[c] = sum over (b, pixel) of dy; `work` (ccb_bias_grad_workspace_floats) lets large planes be reduced in two
  * deterministic stages, without it one block per channel does the whole sum */
 long long ccb_bias_grad_workspace_floats(int B, int C, int plane);

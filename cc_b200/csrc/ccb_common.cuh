@@ -37,12 +37,12 @@ int check_launch(const char* what);
     } while (0)
 
 // ---- weight preparation for the tensor-core conv kernels (wprep.cu) ----
-enum { WPREP_TC = 0, WPREP_TMA = 1, WPREP_SLAB = 2 };
+enum { WPREP_TC = 0, WPREP_TMA = 1, WPREP_SLAB = 2, WPREP_NHWC = 3 };
 struct WPrepDesc {
     const float* w;
     float* wp;
     int N, Cc, KK, Ci, mode, Kp, ntaps;
-    int layout, p0, p1, p2;      // TC: p0 = cpad;  TMA: p0 = cb, p1 = cblocks, p2 = units;  SLAB: p0 = cs, p1 = cblocks, p2 = kt_full
+    int layout, p0, p1, p2;      // TC: p0 = cpad;  TMA: p0 = cb, p1 = cblocks, p2 = units;  SLAB: p0 = cs, p1 = cblocks, p2 = kt_full;  NHWC: p0 = 32, p1 = cblocks, p2 = ntaps
     signed char tap_index[64];
 };
 #ifndef CCB_CPU_SIM

@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcArgs a) 
                 h.x = tf32_hi(av[c][0]); h.y = tf32_hi(av[c][1]); h.z = tf32_hi(av[c][2]); h.w = tf32_hi(av[c][3]);
                 a_hi[tile_idx(r, c, SWZ)] = h;
                 if (THREE) {
-                    l.x = av[c][0] - h.x; l.y = av[c][1] - h.y; l.z = av[c][2] - h.z; l.w = av[c][3] - h.w;
+                    l.x = tf32_hi(av[c][0] - h.x); l.y = tf32_hi(av[c][1] - h.y); l.z = tf32_hi(av[c][2] - h.z); l.w = tf32_hi(av[c][3] - h.w);
                     a_lo[tile_idx(r, c, SWZ)] = l;
                 }
             }
@@ -568,14 +568,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_wgrad_kernel(const TcWg
                 h.x = tf32_hi(av[j][0]); h.y = tf32_hi(av[j][1]); h.z = tf32_hi(av[j][2]); h.w = tf32_hi(av[j][3]);
                 a_hi[tile_idx(r, c, SWZ)] = h;
                 if (THREE) {
-                    l.x = av[j][0] - h.x; l.y = av[j][1] - h.y; l.z = av[j][2] - h.z; l.w = av[j][3] - h.w;
+                    l.x = tf32_hi(av[j][0] - h.x); l.y = tf32_hi(av[j][1] - h.y); l.z = tf32_hi(av[j][2] - h.z); l.w = tf32_hi(av[j][3] - h.w);
                     a_lo[tile_idx(r, c, SWZ)] = l;
                 }
                 if (r < umma_n) {
                     h.x = tf32_hi(bv[j].x); h.y = tf32_hi(bv[j].y); h.z = tf32_hi(bv[j].z); h.w = tf32_hi(bv[j].w);
                     b_hi[tile_idx(r, c, SWZ)] = h;
                     if (THREE) {
-                        l.x = bv[j].x - h.x; l.y = bv[j].y - h.y; l.z = bv[j].z - h.z; l.w = bv[j].w - h.w;
+                        l.x = tf32_hi(bv[j].x - h.x); l.y = tf32_hi(bv[j].y - h.y); l.z = tf32_hi(bv[j].z - h.z); l.w = tf32_hi(bv[j].w - h.w);
                         b_lo[tile_idx(r, c, SWZ)] = l;
                     }
                 }

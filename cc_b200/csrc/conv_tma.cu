@@ -12,11 +12,9 @@
 //     one elected thread issues hi*hi (+ lo*hi + hi*lo into a second TMEM accumulator) and commits.
 //   No register staging of operands, no per-element index math, producers = ONE thread: the pipeline depth is
 //   bounded by shared memory only (3 stages of 64 KB in 3xTF32, 6 stages of 32 KB in single-TF32 mode).
-#include "ccb_common.cuh"
+#include "tc_common.cuh"
 
 #ifndef CCB_CPU_SIM
-#include <cstdlib>
-#include <cuda.h>   // CUtensorMap + enums only; cuTensorMapEncodeTiled is fetched through the runtime (no libcuda link)
 
 namespace ccb {
 
@@ -44,29 +42,6 @@ struct TmaConvArgs {
     signed char off_y[TM_MAX_SLOTS], off_x[TM_MAX_SLOTS];
 };
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void tm_mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void tm_mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void tm_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool tm_mbar_try(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(smem_addr(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
 // A wait that cannot complete is a protocol bug: fail the launch instead of hanging the box.  With the bring-up
 // switch (ccb_debug_tc_swap_strides bit 4) the first timeout is recorded in g_tma_status and every wait of the
 // launch falls through, so that the probe can report WHO waited on WHAT without losing the CUDA context.
@@ -87,101 +62,6 @@ __device__ __forceinline__ void tm_mbar_wait(uint64_t* bar, uint32_t parity, int
         if (spins > (soft ? (1u << 20) : (1u << 26))) { tm_wait_failed(soft, role, it); return; }
     }
 }
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(smem_addr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_addr(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_addr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_addr(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tm_umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// Warp-uniform issue: every lane runs the surrounding code (so descriptors stay in uniform registers and no
-// divergent region is entered), only the leader's predicate lets the instruction through.
-// Descriptors are passed as their two 32-bit halves: the high half is constant per operand kind.
-__device__ __forceinline__ void tm_umma_tf32_p(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                               uint32_t idesc, uint32_t accumulate, uint32_t leader) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p, q;\n\t"
-        ".reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "setp.ne.b32 q, %7, 0;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
-        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
-        : "memory");
-}
-__device__ __forceinline__ void tm_commit_p(uint64_t* bar, uint32_t leader) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred q;\n\t"
-        "setp.ne.b32 q, %1, 0;\n\t"
-        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-        "}" ::"r"(smem_addr(bar)), "r"(leader)
-        : "memory");
-}
-// halves of the shared-memory matrix descriptors (version 1): low = start >> 4 | LBO >> 4 << 16, high = SBO >> 4 | 1 << 14 | layout << 29
-constexpr uint32_t DESC_A_MN_LO = (4096u >> 4) << 16, DESC_A_MN_HI = (512u >> 4) | (1u << 14) | (1u << 29);   // MN-major SWIZZLE_128B_BASE32B
-constexpr uint32_t DESC_K_LO = (16u >> 4) << 16, DESC_K_HI = (1024u >> 4) | (1u << 14) | (2u << 29);          // K-major SWIZZLE_128B
-__device__ __forceinline__ void tm_prefetch_map(const CUtensorMap* m) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
-}
-__device__ __forceinline__ void tm_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void tm_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-// shared-memory matrix descriptor (version 1); layout 2 = SWIZZLE_128B (16 B chunks), 1 = SWIZZLE_128B_BASE32B (32 B
-// chunks, 4-row atoms: the only layout the tensor core accepts for an MN-major tf32 operand)
-__device__ __forceinline__ uint64_t tm_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)layout << 61;
-    return d;
-}
-__device__ __forceinline__ float4 tf32_rest4(const float4 v) {
-    float4 l;
-    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-    return l;
-}
-__device__ __forceinline__ float tm_act(float v, int act, float slope) {
-    switch (act) {
-        case CCB_ACT_RELU: return fmaxf(v, 0.f);
-        case CCB_ACT_LEAKY: return v > 0.f ? v : v * slope;
-        case CCB_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
-        default: return v;
-    }
-}
-
 template <bool THREE>
 __global__ void __launch_bounds__(TM_THREADS, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TmaConvArgs a) {
@@ -306,12 +186,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int i = wt + j * 256;            // 1024 float4 per stage
-                    float4 v = raw[i], l;
-                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                    lo[i] = l;
+                    lo[i] = tf32_rest4(raw[i]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 tm_mbar_arrive(&split_full[s]);
@@ -366,25 +241,18 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
 void launch_splitk_reduce(const float* work, float* out, const float* bias, const float* res, long long numel, int splits,
                           int plane, int C, int act, float slope, cudaStream_t st);   // conv_ffma.cu
+
+// conv_nhwc.cu: channels-last slab kernel
+bool nhwc_applies(const int* off_y, const int* off_x, int ntaps, int in_stride, int Cc, int N, int Hc, int Wc, int three);
+long long nhwc_copy_floats(int B, int Cc, int Hin, int Win);
+long long nhwc_wp_floats(const int* off_y, const int* off_x, int ntaps, int Cc, int N);
+int nhwc_transpose(const float* x, float* xh, int B, int Cc, int Hin, int Win, cudaStream_t st);
+int launch_nhwc(const float* xh, int B, int Cc, int Hin, int Win, const float* w, int mode, int N, int KK, int Ci, const int* off_y,
+                const int* off_x, const int* tap_index, int ntaps, int Hc, int Wc, int Hout, int Wout, int out_stride, int out_oy,
+                int out_ox, const float* bias, const float* res, float* out, int act, float slope, int three, float* work,
+                long long wp_floats, int splits, float* partial, long long out_numel, cudaStream_t st);
 
 static int g_tma_enabled = 1, g_tma_soft = 0;
 void tma_set_enabled(int v) { g_tma_enabled = v & 1; g_tma_soft = (v >> 1) & 1; }
@@ -1265,9 +1133,57 @@ bool tma_direct_fprop(const ccb_conv_desc* d) {
     return direct_applies(oy, ox, nt, d->stride, d->Ci, d->Co, (long long)d->B * d->Ho * d->Wo);
 }
 
+// Does the channels-last kernel take the whole op (FPROP: the one gather; DGRAD: every parity class)?  wpf = prepared
+// weight floats (max over the classes), tiles = CTAs of one launch before split-K.
+static bool nhwc_takes(const ccb_conv_desc* d, int op, long long* wpf_out, long long* tiles_out) {
+    int oy[TM_MAX_SLOTS], ox[TM_MAX_SLOTS], tix[TM_MAX_SLOTS];
+    if (d->kh * d->kw > TM_MAX_SLOTS) return false;
+    long long wpf = 0, tiles = 0;
+    if (op == CCB_CONV_FPROP) {
+        if (d->stride != 1) return false;
+        const int nt = fprop_taps(d, oy, ox, tix);
+        if (direct_applies(oy, ox, nt, 1, d->Ci, d->Co, (long long)d->B * d->Ho * d->Wo)) return false;
+        if (!nhwc_applies(oy, ox, nt, 1, d->Ci, d->Co, d->Ho, d->Wo, 1)) return false;
+        wpf = nhwc_wp_floats(oy, ox, nt, d->Ci, d->Co);
+        tiles = (long long)d->B * cdiv(d->Wo, 8) * cdiv(d->Ho, 16) * cdiv(d->Co, 128);
+    } else {
+        const int s = d->stride;
+        for (int py = 0; py < s && py < d->Hi; ++py)
+            for (int px = 0; px < s && px < d->Wi; ++px) {
+                const int nt = dgrad_taps(d, py, px, oy, ox, tix);
+                const int Hc = (d->Hi - py + s - 1) / s, Wc = (d->Wi - px + s - 1) / s;
+                if (nt < 1) return false;
+                if (direct_applies(oy, ox, nt, 1, d->Co, d->Ci, (long long)d->B * Hc * Wc)) return false;
+                if (!nhwc_applies(oy, ox, nt, 1, d->Co, d->Ci, Hc, Wc, 1)) return false;
+                const long long f = nhwc_wp_floats(oy, ox, nt, d->Co, d->Ci);
+                if (f > wpf) wpf = f;
+            }
+        tiles = (long long)d->B * cdiv(cdiv(d->Wi, s), 8) * cdiv(cdiv(d->Hi, s), 16) * cdiv(d->Ci, 128);
+    }
+    if (wpf < 0) return false;
+    *wpf_out = wpf; *tiles_out = tiles;
+    return true;
+}
+static int nhwc_plan_splits(long long tiles, int cblocks, long long out_numel, long long part_floats) {
+    if (tiles >= 148 || cblocks < 4) return 1;
+    long long s = (2 * 148 + tiles - 1) / tiles;
+    if (s > cblocks / 2) s = cblocks / 2;
+    if (s > 8) s = 8;
+    if (out_numel > 0 && s * out_numel > part_floats) s = part_floats / out_numel;
+    return s < 2 ? 1 : (int)s;
+}
+
 long long tma_workspace_floats(const ccb_conv_desc* d, int op) {
     int oy[TM_MAX_SLOTS], ox[TM_MAX_SLOTS], tix[TM_MAX_SLOTS];
     long long wpf = 0, tiles, out_numel;
+    {
+        long long nwpf, ntiles;
+        if (nhwc_takes(d, op, &nwpf, &ntiles)) {
+            const long long copyf = (op == CCB_CONV_FPROP) ? nhwc_copy_floats(d->B, d->Ci, d->Hi, d->Wi) : nhwc_copy_floats(d->B, d->Co, d->Ho, d->Wo);
+            const long long on = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Co * d->Ho * d->Wo : (long long)d->B * d->Ci * d->Hi * d->Wi;
+            return copyf + nwpf + (ntiles < 148 ? 8 * on : 0);
+        }
+    }
     if (op == CCB_CONV_FPROP) {
         const int nt = fprop_taps(d, oy, ox, tix);
         wpf = tma_wp_floats(oy, ox, nt, d->stride, d->Ci, d->Co, (long long)d->B * d->Ho * d->Wo);
@@ -1320,6 +1236,22 @@ int tma_fprop(const ccb_conv_desc* d, const float* x, const float* w, const floa
     int oy[TM_MAX_SLOTS], ox[TM_MAX_SLOTS], tix[TM_MAX_SLOTS];
     const int nt = fprop_taps(d, oy, ox, tix);
     const long long out_numel = (long long)d->B * d->Co * d->Ho * d->Wo;
+    {
+        long long nwpf, ntiles;
+        if (nhwc_takes(d, CCB_CONV_FPROP, &nwpf, &ntiles)) {                      // channels-last slab kernel
+            const long long copyf = nhwc_copy_floats(d->B, d->Ci, d->Hi, d->Wi);
+            CCB_REQUIRE(copyf + nwpf <= work_floats, CCB_ERR_ARG, "conv_nhwc fprop: workspace too small");
+            int rc = nhwc_transpose(x, work, d->B, d->Ci, d->Hi, d->Wi, st);
+            if (rc) return rc;
+            float* wk = work + copyf;
+            const int splits = nhwc_plan_splits(ntiles, cdiv(d->Ci, 32), out_numel, work_floats - copyf - nwpf);
+            rc = launch_nhwc(work, d->B, d->Ci, d->Hi, d->Wi, w, 0, d->Co, nt, d->Ci, oy, ox, tix, nt, d->Ho, d->Wo, d->Ho, d->Wo, 1, 0, 0, bias,
+                             res, y, d->act, d->slope, three, wk, nwpf, splits, wk + nwpf, out_numel, st);
+            if (rc || splits == 1) return rc;
+            launch_splitk_reduce(wk + nwpf, y, bias, res, out_numel, splits, d->Ho * d->Wo, d->Co, d->act, d->slope, st);
+            return check_launch("conv_nhwc splitk reduce");
+        }
+    }
     const long long wpf = tma_wp_floats(oy, ox, nt, d->stride, d->Ci, d->Co, (long long)d->B * d->Ho * d->Wo);
     const long long padf = tma_pad_floats(d, CCB_CONV_FPROP);
     CCB_REQUIRE(wpf >= 0 && padf >= 0 && padf + wpf <= work_floats, CCB_ERR_ARG, "conv_tma fprop: workspace too small");
@@ -1344,6 +1276,31 @@ int tma_dgrad(const ccb_conv_desc* d, const float* dy, const float* w, const flo
     const int s = d->stride;
     const long long out_numel = (long long)d->B * d->Ci * d->Hi * d->Wi;
     int oy[TM_MAX_SLOTS], ox[TM_MAX_SLOTS], tix[TM_MAX_SLOTS];
+    {
+        long long nwpf, ntiles;
+        if (nhwc_takes(d, CCB_CONV_DGRAD, &nwpf, &ntiles)) {                      // channels-last slab kernel, one copy of dy for all classes
+            const long long copyf = nhwc_copy_floats(d->B, d->Co, d->Ho, d->Wo);
+            CCB_REQUIRE(copyf + nwpf <= work_floats, CCB_ERR_ARG, "conv_nhwc dgrad: workspace too small");
+            int rc = nhwc_transpose(dy, work, d->B, d->Co, d->Ho, d->Wo, st);
+            if (rc) return rc;
+            float* wk = work + copyf;
+            // split-K partials of different parity classes would alias: split only stride-1 problems
+            const int splits = (s == 1) ? nhwc_plan_splits(ntiles, cdiv(d->Co, 32), out_numel, work_floats - copyf - nwpf) : 1;
+            for (int py = 0; py < s && py < d->Hi; ++py)
+                for (int px = 0; px < s && px < d->Wi; ++px) {
+                    const int nt = dgrad_taps(d, py, px, oy, ox, tix);
+                    const int Hc = (d->Hi - py + s - 1) / s, Wc = (d->Wi - px + s - 1) / s;
+                    rc = launch_nhwc(work, d->B, d->Co, d->Ho, d->Wo, w, 1, d->Ci, d->kh * d->kw, d->Ci, oy, ox, tix, nt, Hc, Wc, d->Hi, d->Wi, s,
+                                     py, px, bias, res, dx, d->act, d->slope, three, wk, nwpf, splits, wk + nwpf, out_numel, st);
+                    if (rc) return rc;
+                }
+            if (splits > 1) {
+                launch_splitk_reduce(wk + nwpf, dx, bias, res, out_numel, splits, d->Hi * d->Wi, d->Ci, d->act, d->slope, st);
+                return check_launch("conv_nhwc dgrad splitk reduce");
+            }
+            return CCB_OK;
+        }
+    }
     long long wpf_max = 0;
     for (int py = 0; py < s && py < d->Hi; ++py)
         for (int px = 0; px < s && px < d->Wi; ++px) {

@@ -23,6 +23,13 @@ __device__ __forceinline__ bool wprep_decode(const WPrepDesc& a, int k, int& slo
         c = (unit - slot * a.p1) * a.p0 + j;
         return slot < a.ntaps && c < a.Cc;
     }
+    if (a.layout == WPREP_NHWC) {                     // k-stage = (channel block, slot), 32 channels each (tail zero)
+        const int kt = k >> 5;
+        const int cblock = kt / a.p2;
+        slot = kt - cblock * a.p2;
+        c = cblock * 32 + (k & 31);
+        return cblock < a.p1 && slot < a.ntaps && c < a.Cc;
+    }
     // WPREP_SLAB: k-stage -> (channel block, flattened (slot, channel) index inside the block)
     const int kt = k >> 5;
     const int cblock = min(kt / a.p2, a.p1 - 1);
@@ -62,7 +69,9 @@ __device__ __forceinline__ void wprep_block(const WPrepDesc& a, int nb, int bloc
         const float h = __uint_as_float(hb);
         const long long o = (long long)(n0 + nl) * a.Kp + k;
         a.wp[o] = h;
-        a.wp[plane + o] = v - h;
+        uint32_t lb;                                       // the remainder rounded to tf32 as well: the hardware reads it exactly
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - h));
+        a.wp[plane + o] = __uint_as_float(lb);
     }
 }
 

@@ -260,6 +260,12 @@ void ccb_debug_tc_swap_strides(int swap);
  * out4 = {role (0 = none; 1 producer/empty, 2 mma/tma_full, 3 mma/split_full, 4 split/tma_full, 5 epilogue/accum),
  * k-iteration, blockIdx.x, blockIdx.z} */
 int ccb_debug_tma_status(unsigned int* out4);
+/* bring-up aids of the channels-last slab kernel (conv_nhwc.cu): enabled = 0 routes its problems back to the NCHW kernels
+ * (must produce results within rounding), soft = 1 records barrier time-outs instead of trapping, dbg bit 0 sets the
+ * descriptor base-offset field (must produce wrong results for taps whose slab offset is not a multiple of 8 pixels),
+ * bit 2 sends 1x1 convolutions through it as well.  ccb_debug_nhwc_status: like ccb_debug_tma_status. */
+void ccb_debug_nhwc(int enabled, int soft, int dbg);
+int ccb_debug_nhwc_status(unsigned int* out4);
 /* host-side tiling of the TMA-fed convolution family for one problem (no launch, no driver needed; unit tests):
  * op FPROP / DGRAD (parity class py, px) -> out16 = {kind (2 slab, 3 aligned TMA, 4 direct, -1 none), ...}, WGRAD -> {5, ...};
  * field meaning in conv_tma.cu */

@@ -88,7 +88,12 @@ def case_input_pipeline_fullsize(device, B=4, Hs=256, Ws=832):
     tgt, refs, Kd, Kinv = CI.DeviceAugment(device)(torch.from_numpy(frames), np.broadcast_to(K, (B, 3, 3)).copy(), params=p)
     want, Kw = OT.apply(frames, K, p)
     out = torch.stack(refs[:2] + [tgt] + refs[2:], 1).cpu().numpy()
-    assert np.abs(out - want).max() <= 2e-5
+    # uniform-noise frames: neighbouring pixels differ by up to 2.0 (normalised), so one ulp of an fp32 source coordinate
+    # near x = 900 (6.1e-5) moves a bilinear sample by up to 1.2e-4 - the bound is 2 ulp(coordinate) x the pixel range
+    # (measured 1.3e-4; the smooth golden fixture above holds 2e-5)
+    bound = 2 * float(np.spacing(np.float32(max(p['scaled_w'].max(), p['scaled_h'].max())))) * 2.0
+    err = float(np.abs(out - want).max())
+    assert err <= bound, 'input pipeline full size: max err %.3e > %.3e' % (err, bound)
     assert np.array_equal(Kd.cpu().numpy(), Kw)
     assert tgt.shape == (B, 3, Hs, Ws) and len(refs) == 4 and out.min() >= -1 - 1e-6 and out.max() <= 1 + 1e-6
 

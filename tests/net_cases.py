@@ -162,6 +162,50 @@ def case_conv_tma_family(device):
         cnn.CONV_IMPL = saved
 
 
+def case_conv_nhwc(device):
+    """The channels-last slab kernel (conv_nhwc.cu: NCHW -> NHWC copy, one TMA slab per 32-channel block, filter taps as
+    descriptor offsets into the slab): FPROP, DGRAD (stride 1 and the 4 parity classes of stride 2 / ConvTranspose2d),
+    channel tails (C % 32 != 0), N tails, ragged tile rows / columns, 7x7 and 5x5 halos, split-K over channel blocks.
+    Checked against torch fp64 AND against the NCHW kernels (ccb_debug_nhwc(0, ..) turns the path off).  GPU only."""
+    from cc_b200 import _lib
+    g = torch.Generator().manual_seed(13)
+    shapes = [(2, 64, 32, 40, 64, 3, 1, 1),       # the ResBlock shape: 2 channel blocks
+              (2, 32, 48, 72, 32, 7, 1, 3),       # 7x7 halo (DispResNet6 conv1b), one channel block, N = 32
+              (2, 196, 20, 44, 128, 3, 1, 1),     # Back2Future decoder: channel tail 196 = 6 x 32 + 4, ragged rows / columns
+              (2, 100, 33, 23, 72, 5, 1, 2),      # 5x5, N tail (72), odd sizes
+              (1, 512, 16, 24, 200, 3, 1, 1),     # few tiles, long K: split-K over channel blocks, 2 N tiles
+              (2, 64, 48, 64, 48, 3, 2, 1),       # stride 2: DGRAD parity classes through the kernel (fprop stays NCHW)
+              (2, 96, 40, 56, 64, 4, 2, 1)]       # MaskNet6 deconv geometry (k4 s2 p1) as the conv whose dgrad it is
+    saved = cnn.CONV_IMPL
+    lib = _lib.lib()
+    try:
+        cnn.CONV_IMPL = _lib.IMPL_TC
+        for (B, Ci, H, W, Co, k, s, p) in shapes:
+            tag = f'nhwc {Ci}->{Co} k{k} s{s} {H}x{W}'
+            x = torch.randn(B, Ci, H, W, generator=g).to(device).requires_grad_(True)
+            w = (torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5).to(device).requires_grad_(True)
+            b = torch.randn(Co, generator=g).to(device).requires_grad_(True)
+            xd, wd, bd = [t.detach().double().requires_grad_(True) for t in (x, w, b)]
+            zd = F.conv2d(xd, wd, bd, s, p)
+            wt = _wts(zd.shape, 9, device)
+            gd = torch.autograd.grad((zd * wt.double()).sum(), [xd, wd, bd])
+            outs = {}
+            for on in (1, 0):
+                lib.ccb_debug_nhwc(on, 0, 0)
+                # fused epilogue (bias + LeakyReLU) in the forward; gradients with a linear epilogue (see case_conv_tc)
+                assert_close(cnn.conv2d(x, w, b, None, s, p, 'leaky', 0.2), F.leaky_relu(zd, 0.2), 1e-4, f'{tag} nhwc={on} fprop+leaky')
+                y = cnn.conv2d(x, w, b, None, s, p, None, 0.2)
+                gx, gw, gb = torch.autograd.grad((y * wt).sum(), [x, w, b])
+                outs[on] = (y.detach(), gx, gw, gb)
+                for got, ref, what in zip(outs[on], (zd,) + tuple(gd), ('fprop', 'dgrad', 'wgrad', 'bias grad')):
+                    assert_close(got, ref, 1e-4, f'{tag} nhwc={on} {what}')
+            for a_, b_, what in zip(outs[1], outs[0], ('fprop', 'dgrad', 'wgrad', 'bias grad')):
+                assert_close(a_, b_, 1e-4, f'{tag} channels-last vs NCHW kernels {what}')
+    finally:
+        lib.ccb_debug_nhwc(1, 0, 0)
+        cnn.CONV_IMPL = saved
+
+
 def case_bn_upsample(device):
     g = torch.Generator().manual_seed(1)
     x = torch.randn(3, 6, 5, 7, generator=g).to(device).requires_grad_(True)

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, 'cc_b200', 'csrc')
 OUT = os.path.join(HERE, 'libccb200_sim.so')
-SIM_SOURCES = ['common.cu', 'photo.cu', 'warp_ops.cu', 'smooth_bce.cu', 'conv_ffma.cu', 'conv_tc.cu', 'conv_tma.cu', 'wprep.cu', 'misc_ops.cu', 'b2f_ops.cu', 'io_ops.cu']
+SIM_SOURCES = ['common.cu', 'photo.cu', 'warp_ops.cu', 'smooth_bce.cu', 'conv_ffma.cu', 'conv_tc.cu', 'conv_tma.cu', 'conv_nhwc.cu', 'wprep.cu', 'misc_ops.cu', 'b2f_ops.cu', 'io_ops.cu']
 
 
 def build(force=False):

@@ -97,6 +97,10 @@ def test_conv_tma_family():
     NC.case_conv_tma_family(torch.device('cuda:0'))
 
 
+def test_conv_nhwc_slab():
+    NC.case_conv_nhwc(torch.device('cuda:0'))
+
+
 def test_joint_step_cfg3_vs_oracle():
     SC.case_step_cfg3(torch.device('cuda:0'))
 

@@ -293,7 +293,10 @@ def profile_pass(trainer, tgt, refs, K, Kinv, steps=2):
                 s.record()
                 rc = fn(*a)
                 e.record()
-                records.append((name, a[0], s, e))
+                kern = None
+                if name.startswith('ccb_conv2d_'):
+                    kern = (real.ccb_debug_last_conv_kernel() or b'').decode() + ':' + name[len('ccb_conv2d_'):]
+                records.append((name, a[0], s, e, kern))
                 return rc
             return wrapped
 
@@ -308,15 +311,18 @@ def profile_pass(trainer, tgt, refs, K, Kinv, steps=2):
         finally:
             _lib._lib = saved
         torch.cuda.synchronize()
-    fam = {}
-    for name, a0, s, e in records:
+    fam, kern_ms = {}, {}
+    for name, a0, s, e, kern in records:
         ms = s.elapsed_time(e)
         f = fam.setdefault(name, dict(ms=0.0, calls=0, flops=0.0, bytes=0.0))
         f['ms'] += ms
         f['calls'] += 1
         if name.startswith('ccb_conv2d_'):
             d = a0._obj if hasattr(a0, '_obj') else a0
-            f['flops'] += 2.0 * d.B * d.Co * d.Ho * d.Wo * d.Ci * d.kh * d.kw
+            fl = 2.0 * d.B * d.Co * d.Ho * d.Wo * d.Ci * d.kh * d.kw
+            f['flops'] += fl
+            k = kern_ms.setdefault(kern, dict(ms=0.0, calls=0, flops=0.0))
+            k['ms'] += ms; k['calls'] += 1; k['flops'] += fl
         elif name.startswith('ccb_photo_loss_'):
             d = a0._obj if hasattr(a0, '_obj') else a0
             px = sum(d.B * d.h[l] * d.w[l] for l in range(d.nlevels))
@@ -349,8 +355,18 @@ def profile_pass(trainer, tgt, refs, K, Kinv, steps=2):
                                    'share_of_step': photo_ms / total, 'peak_source': pk['source']}
     # `roofline` = the heaviest single kernel, timed alone (spec); the aggregated convolution family moves to
     # `roofline_family` (its share of the step is what explains the headline)
+    # live shares of the convolution kernels: CUDA events around every conv call of the eager step, bucketed by the kernel the
+    # call dispatched to (ccb_debug_last_conv_kernel); a call's time includes its helper launches (layout copy, split-K sum)
+    js['conv_kernel_shares'] = {k: {'share_of_step': round(v['ms'] / total, 4), 'calls_per_step': v['calls'] // steps,
+                                    'algorithmic_tflops': round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1)}
+                                for k, v in sorted(kern_ms.items(), key=lambda kv: -kv[1]['ms'])}
     try:
         single = single_kernel_roofline(pk)
+        nh = [v for k, v in kern_ms.items() if k.startswith('conv_nhwc')]
+        if nh:
+            single['share_of_step'] = sum(v['ms'] for v in nh) / total
+            single['share_source'] = 'live: CUDA events around every conv call of the profiled eager step that dispatched to conv_nhwc_kernel (fprop + dgrad)'
+
         if 'roofline' in js:
             js['roofline_family'] = js['roofline']
             single['family_share_of_step'] = js['roofline']['share_of_step']

@@ -109,6 +109,7 @@ _SIGS = {
     'ccb_bias_grad': (_I, [_P, _P, _I, _I, _I, _P, _LL, _P]),
     'ccb_debug_tc_swap_strides': (None, [_I]),
     'ccb_debug_tma_status': (_I, [C.POINTER(C.c_uint)]),
+    'ccb_debug_last_conv_kernel': (C.c_char_p, []),
     'ccb_debug_nhwc': (None, [_I, _I, _I]),
     'ccb_debug_nhwc_status': (_I, [C.POINTER(C.c_uint)]),
     'ccb_debug_conv_plan': (_I, [C.POINTER(ConvDesc), _I, _I, _I, C.POINTER(_I)]),

@@ -6,6 +6,7 @@ namespace ccb {
 
 static thread_local char g_err[512] = "";
 long long g_launches = 0;
+static thread_local const char* g_last_conv = "";    // main kernel of the last convolution call (bench.py kernel shares)
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -15,6 +16,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int check_launch(const char* what) {
+    if (strncmp(what, "conv_", 5) == 0 && !strstr(what, "reduce") && !strstr(what, "pad")) g_last_conv = what;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: CUDA error: %s", what, cudaGetErrorString(e));
@@ -27,6 +29,7 @@ int check_launch(const char* what) {
 
 extern "C" const char* ccb_last_error_string(void) { return ccb::g_err; }
 extern "C" int ccb_version(void) { return 100; }
+extern "C" const char* ccb_debug_last_conv_kernel(void) { return ccb::g_last_conv; }
 extern "C" long long ccb_launch_count(void) { return ccb::g_launches; }
 extern "C" int ccb_is_simulator(void) {
 #ifdef CCB_CPU_SIM

@@ -260,6 +260,9 @@ void ccb_debug_tc_swap_strides(int swap);
  * out4 = {role (0 = none; 1 producer/empty, 2 mma/tma_full, 3 mma/split_full, 4 split/tma_full, 5 epilogue/accum),
  * k-iteration, blockIdx.x, blockIdx.z} */
 int ccb_debug_tma_status(unsigned int* out4);
+/* which kernel the last convolution call of this thread launched ("conv_nhwc", "conv_slab", "conv_tma", "conv_direct", "conv_tc",
+ * "conv_slab_wgrad", "conv_tc_wgrad", "conv2d_fprop" ... for the CUDA-core GEMM): bench.py buckets its per-call timings by it */
+const char* ccb_debug_last_conv_kernel(void);
 /* bring-up aids of the channels-last slab kernel (conv_nhwc.cu): enabled = 0 routes its problems back to the NCHW kernels
  * (must produce results within rounding), soft = 1 records barrier time-outs instead of trapping, dbg bit 0 sets the
  * descriptor base-offset field (must produce wrong results for taps whose slab offset is not a multiple of 8 pixels),

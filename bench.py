@@ -379,11 +379,12 @@ def profile_pass(trainer, tgt, refs, K, Kinv, steps=2):
 
 
 def single_kernel_roofline(pk, iters=20):
-    """The heaviest single kernel of the step, alone: conv_slab_kernel on DispResNet6's 7x7 32->32 layer (b4, 128x416).
-    Duration = CUDA events around `iters` launches on the launching stream (inputs 27 MB + outputs 27 MB per launch,
-    weights re-prepared every launch as in the step); DRAM traffic = the committed ncu --set full capture of the same
-    launch (profiles/r01_ncu_final_key_metrics.json), null if that file is absent."""
-    from cc_b200 import nn as cnn
+    """The heaviest single convolution of the step, alone: DispResNet6's 7x7 32->32 layer (b4, 128x416, 21.4 GFLOP), which
+    the dispatcher gives to conv_nhwc_kernel (channels-last slab kernel).  Duration = CUDA events around `iters` calls on
+    the launching stream - a call = NCHW->NHWC copy + weight preparation + the kernel, as in the step (inputs 27 MB +
+    outputs 27 MB per launch).  DRAM traffic = the committed ncu --set full capture of the same launch
+    (profiles/r02_ncu_nhwc_7x7.txt), labelled as such; null if that file is absent."""
+    from cc_b200 import nn as cnn, _lib
     dev = torch.device('cuda', torch.cuda.current_device())
     B, C, Hh, Ww, k = PER_GPU_BATCH, 32, H // 2, W // 2, 7
     x = torch.randn(B, C, Hh, Ww, device=dev)
@@ -392,6 +393,7 @@ def single_kernel_roofline(pk, iters=20):
     with torch.no_grad():
         for _ in range(3):
             cnn.conv2d(x, w, b, None, 1, 3, 'relu')
+        kern = (_lib.lib().ccb_debug_last_conv_kernel() or b'').decode()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(iters):
@@ -401,25 +403,25 @@ def single_kernel_roofline(pk, iters=20):
     us = e0.elapsed_time(e1) * 1e3 / iters
     flops = 2.0 * B * C * C * k * k * Hh * Ww
     ach = flops / (us * 1e-6) / 1e12
-    traffic = None
+    traffic, traffic_src = None, None
     try:
-        km = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_final_key_metrics.json')))['slab']
         unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-        traffic = sum(float(km[m][0]) * unit[km[m][1]] for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+        vals = {}
+        for line in open(os.path.join(ROOT, 'profiles', 'r02_ncu_nhwc_7x7.txt')):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                vals[f[0]] = float(f[1]) * unit[f[2]]
+        if len(vals) == 2:
+            traffic = sum(vals.values())
+            traffic_src = 'committed capture profiles/r02_ncu_nhwc_7x7.txt (ncu --set full of this launch, kernel only), not re-measured in this run'
     except Exception:
         pass
-    share = None
-    try:
-        for line in open(os.path.join(ROOT, 'profiles', 'r01_launches_final_summary.txt')):
-            if line.startswith('conv_slab_kernel'):
-                share = float(line.split('%')[0].split()[-1]) / 100.0
-    except Exception:
-        pass
-    return {'bound': 'tensor', 'kernel': 'conv_slab_kernel<3xTF32> + wprep (7x7 32->32 fprop, b%d %dx%d)' % (B, Hh, Ww),
-            'share_of_step': share, 'share_source': 'all conv_slab_kernel launches of one step, ncu launch list (profiles/r01_launches_final_summary.txt)',
+    return {'bound': 'tensor', 'kernel': '%s_kernel<3xTF32> + layout copy + weight prep (7x7 32->32 fprop, b%d %dx%d)' % (kern, B, Hh, Ww),
+            'share_of_step': None, 'share_source': None,
             'achieved': ach, 'peak': pk['tensor_burst'], 'unit': 'TFLOP/s', 'frac': ach / pk['tensor_burst'],
             'us_per_launch': us, 'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': 2.0 * B * C * Hh * Ww * 4,
-            'traffic': traffic, 'peak_source': pk['source'] + ' bf16 burst (kernel timed alone); 3 tf32 passes: ceiling = peak / 6'}
+            'traffic': traffic, 'traffic_source': traffic_src,
+            'peak_source': pk['source'] + ' bf16 burst (kernel timed alone); 3 tf32 passes at half the bf16 rate: ceiling = peak / 6'}
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -42,7 +42,7 @@ struct NhwcArgs {
     float* out;
     int act;
     float slope;
-    int nstages, nbox, soft, dbg;
+    int nstages, nbox, ntile_w, tmem_cols, soft, dbg;    // ntile_w: output channels per CTA (64 or 128)
     signed char off_y[NH_MAX_TAPS], off_x[NH_MAX_TAPS];
 };
 
@@ -67,7 +67,7 @@ __device__ __forceinline__ void nh_wait(uint64_t* bar, uint32_t parity, int soft
 }
 
 template <bool THREE>
-__global__ void __launch_bounds__(NH_THREADS, 1)
+__global__ void __launch_bounds__(NH_THREADS, 2)
 conv_nhwc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b, const NhwcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
@@ -94,8 +94,8 @@ conv_nhwc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     t -= b * per_b;
     const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
     const int x0 = tx * NH_TW, y0 = ty * NH_TH * a.mt;             // a CTA owns mt vertically stacked 16 x 8 tiles (one slab)
-    const int n0 = blockIdx.y * 128;
-    const int ntile = min(128, a.Ntot - n0);
+    const int n0 = blockIdx.y * a.ntile_w;
+    const int ntile = min(a.ntile_w, a.Ntot - n0);
     const int cb_beg = blockIdx.z * a.cb_per_split;
     const int cb_end = min(a.cblocks, cb_beg + a.cb_per_split);
     const int nblocks = max(0, cb_end - cb_beg);
@@ -120,7 +120,7 @@ conv_nhwc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"((uint32_t)a.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -277,7 +277,7 @@ conv_nhwc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
     }
 }
 
@@ -303,17 +303,21 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 }
 
 static int g_nhwc_enabled = 1, g_nhwc_soft = 0, g_nhwc_dbg = 0;
-void nhwc_set_debug(int enabled, int soft, int dbg);
 
 struct NhwcPlan {
-    int Cp, cblocks, SH, SW, mt, ox_lo, oy_lo, slab_bytes, slab_tx, nslab, nstages, nbox, smem, Kp;
+    int Cp, cblocks, SH, SW, mt, ox_lo, oy_lo, slab_bytes, slab_tx, nslab, nstages, nbox, ntile_w, tmem_cols, smem, Kp;
     bool ok;
 };
 static int g_nhwc_mt = 0;          // bring-up: force the number of stacked tiles (0 = planned)
-void nhwc_set_debug(int enabled, int soft, int dbg) { g_nhwc_enabled = enabled; g_nhwc_soft = soft; g_nhwc_dbg = dbg & 7; g_nhwc_mt = (dbg >> 4) & 7; }
+void nhwc_set_debug(int enabled, int soft, int dbg) { g_nhwc_enabled = enabled; g_nhwc_soft = soft; g_nhwc_dbg = dbg & 15; g_nhwc_mt = (dbg >> 4) & 7; }
 // tap offsets (pixels of the gathered tensor), channels, output channels, output grid -> tiling; !ok: the path does not take
-// this problem.  Stacked tiles (mt > 1, one taller slab, mt accumulator sets in TMEM) reuse every weight tile mt times:
-// weight tiles are the dominant L2 -> shared-memory stream (2 x nbox x 128 B per k-stage against slab_bytes / ntaps).
+// this problem.
+//   * Two CTAs per SM (<= 111 KB of shared memory, <= 256 TMEM columns each) whenever the problem allows: prologue
+//     (barriers, TMEM, first slab) and epilogue (TMEM -> registers -> NCHW stores) of one CTA then hide under the main loop
+//     of the other; measured (ncu, 128 -> 128 3x3): tensor pipe 45 % with one CTA per SM, MMA floor 14 us of a 37 us tile.
+//     More than 64 output channels are cut into 64-wide CTAs for it (grid.y).
+//   * Stacked tiles (mt > 1, one taller slab, mt accumulator sets in TMEM) reuse every weight tile mt times; used for
+//     thin layers on large maps when everything still fits.
 static NhwcPlan nhwc_plan(const int* off_y, const int* off_x, int ntaps, int Cc, int N, int three, int Hc = 0, long long tiles1 = 0) {
     NhwcPlan p;
     memset(&p, 0, sizeof(p));
@@ -329,33 +333,38 @@ static NhwcPlan nhwc_plan(const int* off_y, const int* off_x, int ntaps, int Cc,
     p.Cp = (Cc + 3) & ~3;
     p.cblocks = cdiv(Cc, 32);
     p.Kp = p.cblocks * ntaps * 32;
-    const int ntile = N < 128 ? N : 128;
-    p.nbox = (ntile + 15) & ~15;
-    const int b_stage = (three ? 2 : 1) * p.nbox * 128;
-    const int total = 224 * 1024 - 2048;                          // barriers + tap table + alignment slack
-    // stacked tiles: only while the grid keeps >= 2 CTAs per SM worth of tiles and the map is tall enough
     int mt_max = 1;
     if (g_nhwc_mt > 0) mt_max = g_nhwc_mt;
     else
         for (int mt = 2; mt <= 4; mt *= 2)
-            if (Hc >= NH_TH * mt && tiles1 / mt >= 2 * 148) mt_max = mt;
-    for (int mt = mt_max; mt >= 1 && !p.ok; mt >>= 1) {
-        if (mt * 3 * p.nbox > 512) continue;
-        const int SH = NH_TH * mt + (oyh - oyl);
-        if (SH > 256) continue;
-        const int tx = SH * p.SW * 128;
-        const int sbytes = (tx + 1023) & ~1023;                   // slab bases stay 1024-byte aligned (TMA swizzle atom)
-        for (int nslab = (p.cblocks > 1 ? 2 : 1); nslab >= 1 && !p.ok; --nslab) {
-            const int slabs = (three ? 2 : 1) * nslab * sbytes;
-            int nst = (total - slabs) / b_stage;
-            if (nst > 8) nst = 8;
-            if (nst >= (mt > 1 ? 3 : 2)) {
-                p.mt = mt; p.SH = SH; p.slab_tx = tx; p.slab_bytes = sbytes; p.nslab = nslab; p.nstages = nst; p.ok = true;
+            if (Hc >= NH_TH * mt && tiles1 / mt >= 4 * 148) mt_max = mt;
+    // candidate configurations in order of preference: two CTAs per SM first
+    for (int pass = (g_nhwc_dbg & 8) ? 1 : 0; pass < 2 && !p.ok; ++pass) {
+        const bool two = (pass == 0);
+        const int ntile_w = two ? 64 : 128;
+        const int ntile = N < ntile_w ? N : ntile_w;
+        const int nbox = (ntile + 15) & ~15;
+        const int b_stage = (three ? 2 : 1) * nbox * 128;
+        const int total = (two ? 111 : 224) * 1024 - 2048;        // barriers + tap table + alignment slack
+        for (int mt = mt_max; mt >= 1 && !p.ok; mt >>= 1) {
+            if (mt * (three ? 3 : 1) * nbox > (two ? 256 : 512)) continue;
+            const int SH = NH_TH * mt + (oyh - oyl);
+            if (SH > 256) continue;
+            const int tx = SH * p.SW * 128;
+            const int sbytes = (tx + 1023) & ~1023;               // slab bases stay 1024-byte aligned (TMA swizzle atom)
+            for (int nslab = (p.cblocks > 1 ? 2 : 1); nslab >= 1 && !p.ok; --nslab) {
+                const int slabs = (three ? 2 : 1) * nslab * sbytes;
+                int nst = (total - slabs) / b_stage;
+                if (nst > 8) nst = 8;
+                if (nst >= 3 || (nst >= 2 && !two && mt == 1)) {
+                    p.mt = mt; p.SH = SH; p.slab_tx = tx; p.slab_bytes = sbytes; p.nslab = nslab; p.nstages = nst; p.nbox = nbox;
+                    p.ntile_w = ntile_w; p.tmem_cols = two ? 256 : 512;
+                    p.smem = slabs + nst * b_stage + 2048 + 1024;
+                    p.ok = true;
+                }
             }
         }
     }
-    if (!p.ok) return p;
-    p.smem = (three ? 2 : 1) * p.nslab * p.slab_bytes + p.nstages * b_stage + 2048 + 1024;
     return p;
 }
 
@@ -405,7 +414,7 @@ int launch_nhwc(const float* xh, int B, int Cc, int Hin, int Win, const float* w
     a.splits = splits; a.cb_per_split = cdiv(p.cblocks, splits);
     a.out_numel = out_numel; a.partial = partial;
     a.bias = bias; a.res = res; a.out = out; a.act = act; a.slope = slope; a.soft = g_nhwc_soft; a.dbg = g_nhwc_dbg;
-    a.nstages = p.nstages; a.nbox = p.nbox;
+    a.nstages = p.nstages; a.nbox = p.nbox; a.ntile_w = p.ntile_w; a.tmem_cols = p.tmem_cols;
     WPrepDesc pa;
     memset(&pa, 0, sizeof(pa));
     for (int t = 0; t < NH_MAX_TAPS; ++t) {
@@ -439,7 +448,7 @@ int launch_nhwc(const float* xh, int B, int Cc, int Hin, int Win, const float* w
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         CCB_REQUIRE(r == CUDA_SUCCESS, CCB_ERR_LAUNCH, "conv_nhwc: cuTensorMapEncodeTiled(w) failed (%d)", (int)r);
     }
-    dim3 grid(B * a.tiles_x * a.tiles_y, cdiv(N, 128), splits);
+    dim3 grid(B * a.tiles_x * a.tiles_y, cdiv(N, p.ntile_w), splits);
     auto kfn = three ? conv_nhwc_kernel<true> : conv_nhwc_kernel<false>;
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     CCB_LAUNCH(kfn, grid, dim3(NH_THREADS), p.smem, st, map_x, map_b, a);
@@ -452,7 +461,7 @@ using namespace ccb;
 
 // bring-up: enabled (0 turns the channels-last kernel off), soft (barrier time-outs are recorded, not trapped),
 // dbg bit 0: descriptors WITH the base-offset field (wrong results for unaligned taps), bit 2: 1x1 convolutions take this path
-// too, bits 4-6: force that many stacked tiles per CTA
+// too, bit 3: one CTA per SM (the 128-wide configuration) only, bits 4-6: force that many stacked tiles per CTA
 extern "C" void ccb_debug_nhwc(int enabled, int soft, int dbg) { nhwc_set_debug(enabled, soft, dbg); }
 extern "C" int ccb_debug_nhwc_status(unsigned int* out4) {
     cudaDeviceSynchronize();

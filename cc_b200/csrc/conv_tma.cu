@@ -1145,7 +1145,7 @@ static bool nhwc_takes(const ccb_conv_desc* d, int op, long long* wpf_out, long 
         if (direct_applies(oy, ox, nt, 1, d->Ci, d->Co, (long long)d->B * d->Ho * d->Wo)) return false;
         if (!nhwc_applies(oy, ox, nt, 1, d->Ci, d->Co, d->Ho, d->Wo, 1)) return false;
         wpf = nhwc_wp_floats(oy, ox, nt, d->Ci, d->Co);
-        tiles = (long long)d->B * cdiv(d->Wo, 8) * cdiv(d->Ho, 16) * cdiv(d->Co, 128);
+        tiles = (long long)d->B * cdiv(d->Wo, 8) * cdiv(d->Ho, 16) * cdiv(d->Co, 64);
     } else {
         const int s = d->stride;
         for (int py = 0; py < s && py < d->Hi; ++py)
@@ -1158,15 +1158,15 @@ static bool nhwc_takes(const ccb_conv_desc* d, int op, long long* wpf_out, long 
                 const long long f = nhwc_wp_floats(oy, ox, nt, d->Co, d->Ci);
                 if (f > wpf) wpf = f;
             }
-        tiles = (long long)d->B * cdiv(cdiv(d->Wi, s), 8) * cdiv(cdiv(d->Hi, s), 16) * cdiv(d->Ci, 128);
+        tiles = (long long)d->B * cdiv(cdiv(d->Wi, s), 8) * cdiv(cdiv(d->Hi, s), 16) * cdiv(d->Ci, 64);
     }
     if (wpf < 0) return false;
     *wpf_out = wpf; *tiles_out = tiles;
     return true;
 }
 static int nhwc_plan_splits(long long tiles, int cblocks, long long out_numel, long long part_floats) {
-    if (tiles >= 148 || cblocks < 4) return 1;
-    long long s = (2 * 148 + tiles - 1) / tiles;
+    if (tiles >= 2 * 148 || cblocks < 4) return 1;               // two CTAs per SM
+    long long s = (3 * 148 + tiles - 1) / tiles;
     if (s > cblocks / 2) s = cblocks / 2;
     if (s > 8) s = 8;
     if (out_numel > 0 && s * out_numel > part_floats) s = part_floats / out_numel;
@@ -1181,7 +1181,7 @@ long long tma_workspace_floats(const ccb_conv_desc* d, int op) {
         if (nhwc_takes(d, op, &nwpf, &ntiles)) {
             const long long copyf = (op == CCB_CONV_FPROP) ? nhwc_copy_floats(d->B, d->Ci, d->Hi, d->Wi) : nhwc_copy_floats(d->B, d->Co, d->Ho, d->Wo);
             const long long on = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Co * d->Ho * d->Wo : (long long)d->B * d->Ci * d->Hi * d->Wi;
-            return copyf + nwpf + (ntiles < 148 ? 8 * on : 0);
+            return copyf + nwpf + (ntiles < 2 * 148 ? 8 * on : 0);
         }
     }
     if (op == CCB_CONV_FPROP) {

@@ -91,7 +91,7 @@ def run_case(i):
         return e0.elapsed_time(e1) / 20 * 1e3
     gflop = 2.0 * B * zd.shape[2] * zd.shape[3] * Co * Ci * k * k / 1e9
     gy = wt
-    for name, on, dbg in (('auto', 1, 0), ('mt1', 1, 1 << 4), ('mt2', 1, 2 << 4), ('mt4', 1, 4 << 4), ('nchw', 0, 0)):
+    for name, on, dbg in (('auto', 1, 0), ('one', 1, 8), ('one_mt2', 1, 8 | (2 << 4)), ('mt2', 1, 2 << 4), ('nchw', 0, 0)):
         lib.ccb_debug_nhwc(on, 1, dbg)
         with torch.no_grad():
             tf = timed(lambda: cnn.conv2d(x, w, b, None, s, p, 'relu', 0.0))

@@ -370,14 +370,16 @@ static NhwcPlan nhwc_plan(const int* off_y, const int* off_x, int ntaps, int Cc,
 
 // Does the channels-last kernel take this gather?  (measured dispatch: everything with >= 32 gathered channels whose
 // output grid fills 16 x 8 tiles reasonably)
-bool nhwc_applies(const int* off_y, const int* off_x, int ntaps, int in_stride, int Cc, int N, int Hc, int Wc, int three) {
+// `part_of_set`: one parity class of a strided DGRAD whose other classes need the channels-last copy anyway
+bool nhwc_applies(const int* off_y, const int* off_x, int ntaps, int in_stride, int Cc, int N, int Hc, int Wc, int three, bool part_of_set) {
     if (!g_nhwc_enabled || in_stride != 1 || get_encode() == nullptr) return false;
-    if (Cc < 32 || N < 16) return false;
-    if (ntaps == 1 && off_x[0] == 0 && off_y[0] == 0 && !(g_nhwc_dbg & 4)) return false;   // 1x1: the aligned NCHW TMA kernel needs no copy
+    if (Cc < ((g_nhwc_dbg & 2) ? 16 : 32) || N < 16) return false;
+    if (ntaps == 1 && off_x[0] == 0 && off_y[0] == 0 && !part_of_set && !(g_nhwc_dbg & 4)) return false;   // 1x1: the aligned NCHW TMA kernel needs no copy
     if (Hc < 12 || Wc < 7) return false;
     if ((long long)cdiv(Hc, NH_TH) * NH_TH * cdiv(Wc, NH_TW) * NH_TW * 10 > (long long)Hc * Wc * 14) return false;   // > 40 % tile waste
     return nhwc_plan(off_y, off_x, ntaps, Cc, N, three).ok;
 }
+bool nhwc_prefers_thin() { return (g_nhwc_dbg & 2) != 0; }
 long long nhwc_copy_floats(int B, int Cc, int Hin, int Win) { return (long long)B * Hin * Win * ((Cc + 3) & ~3); }
 long long nhwc_wp_floats(const int* off_y, const int* off_x, int ntaps, int Cc, int N) {
     const NhwcPlan p = nhwc_plan(off_y, off_x, ntaps, Cc, N, 1);
@@ -460,7 +462,8 @@ int launch_nhwc(const float* xh, int B, int Cc, int Hin, int Win, const float* w
 using namespace ccb;
 
 // bring-up: enabled (0 turns the channels-last kernel off), soft (barrier time-outs are recorded, not trapped),
-// dbg bit 0: descriptors WITH the base-offset field (wrong results for unaligned taps), bit 2: 1x1 convolutions take this path
+// dbg bit 0: descriptors WITH the base-offset field (wrong results for unaligned taps), bit 1: thin layers (16 .. 31 gathered
+// channels) take this path instead of the CUDA-core direct kernel, bit 2: 1x1 convolutions take this path
 // too, bit 3: one CTA per SM (the 128-wide configuration) only, bits 4-6: force that many stacked tiles per CTA
 extern "C" void ccb_debug_nhwc(int enabled, int soft, int dbg) { nhwc_set_debug(enabled, soft, dbg); }
 extern "C" int ccb_debug_nhwc_status(unsigned int* out4) {
@@ -474,7 +477,8 @@ extern "C" int ccb_debug_nhwc_status(unsigned int* out4) {
 }
 #else
 namespace ccb {
-bool nhwc_applies(const int*, const int*, int, int, int, int, int, int, int) { return false; }
+bool nhwc_applies(const int*, const int*, int, int, int, int, int, int, int, bool) { return false; }
+bool nhwc_prefers_thin() { return false; }
 long long nhwc_copy_floats(int, int, int, int) { return 0; }
 long long nhwc_wp_floats(const int*, const int*, int, int, int) { return -1; }
 }

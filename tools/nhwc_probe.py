@@ -31,6 +31,12 @@ CASES = [  # B, Ci, H, W, Co, k, s, p
     (4, 64, 64, 208, 32, 3, 1, 1),
     (4, 129, 64, 208, 64, 3, 1, 1),
     (4, 65, 128, 416, 32, 3, 1, 1),
+    (4, 16, 256, 832, 16, 3, 1, 1),       # 17: thin layers (dbg bit 1 routes them here instead of the direct kernel)
+    (4, 17, 256, 832, 16, 3, 1, 1),
+    (4, 16, 128, 416, 16, 3, 1, 1),
+    (4, 32, 128, 416, 16, 3, 1, 1),
+    (4, 32, 64, 208, 64, 3, 2, 1),        # 21: stride 2: dgrad classes
+    (4, 16, 128, 416, 32, 3, 2, 1),
 ]
 
 
@@ -57,17 +63,17 @@ def run_case(i):
     xd = x.detach().double().requires_grad_(True)
     gxd, = torch.autograd.grad((F.conv2d(xd, w.detach().double(), b.double(), s, p) * wt.double()).sum(), [xd])
     st = (C.c_uint * 4)()
-    for dbg in (0, 1):
+    for dbg in (0, 2):
         lib.ccb_debug_nhwc(1, 1, dbg)
         y = cnn.conv2d(x, w, b, None, s, p, None, 0.0)
         gx, = torch.autograd.grad((y * wt).sum(), [x])
         torch.cuda.synchronize()
         lib.ccb_debug_nhwc_status(st)
-        out['dbg%d' % dbg] = dict(fprop=rel(y.detach(), zd), dgrad=rel(gx, gxd), status=list(st))
+        out['dbg%d' % (0 if dbg == 0 else 1)] = dict(fprop=rel(y.detach(), zd), dgrad=rel(gx, gxd), status=list(st))
     # per-tap: one-hot filters (small cases only)
     if B * H * W <= 8192 and s == 1:
         taps = {}
-        for dbg in (0, 1):
+        for dbg in (0,):
             lib.ccb_debug_nhwc(1, 1, dbg)
             errs = []
             for t in range(k * k):
@@ -91,7 +97,7 @@ def run_case(i):
         return e0.elapsed_time(e1) / 20 * 1e3
     gflop = 2.0 * B * zd.shape[2] * zd.shape[3] * Co * Ci * k * k / 1e9
     gy = wt
-    for name, on, dbg in (('auto', 1, 0), ('one', 1, 8), ('one_mt2', 1, 8 | (2 << 4)), ('mt2', 1, 2 << 4), ('nchw', 0, 0)):
+    for name, on, dbg in (('auto', 1, 0), ('thin', 1, 2), ('thin_mt4', 1, 2 | (4 << 4)), ('one', 1, 8), ('nchw', 0, 0)):
         lib.ccb_debug_nhwc(on, 1, dbg)
         with torch.no_grad():
             tf = timed(lambda: cnn.conv2d(x, w, b, None, s, p, 'relu', 0.0))

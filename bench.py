@@ -137,6 +137,9 @@ def measure_cfg(cfg, args, dev, rank, local, world, steps, full):
     _say('%s: eager steps' % cfg)
     pyramid.clear()
     trainer.step(tgt, refs, K, Kinv)
+    if getattr(trainer, 'wcache', None) is not None and not trainer.wcache.committed:
+        pyramid.clear()                       # N > 1: the first step taught the gradient buckets, this one records the weight cache
+        trainer.step(tgt, refs, K, Kinv)
     c0 = _lib.lib().ccb_launch_count()
     pyramid.clear()
     trainer.step(tgt, refs, K, Kinv)

@@ -71,7 +71,7 @@ def allreduce_grads(opt):
     opt.grad_scale = 1.0 / w
 
 
-BUCKET_MB = 32.0
+BUCKET_MB = float(os.environ.get('CCB_BUCKET_MB', '32'))
 
 
 class _Bucket:

@@ -116,7 +116,10 @@ class Trainer:
         from . import nn as cnn
         self.opt.zero_grad()
         self.buckets.begin()
-        cnn.WCACHE = self.wcache.h if self.wcache is not None else None
+        # the weight cache keys its copies by parameter address: it starts recording only after the bucket scheduler has
+        # re-packed the flat buffers (its learning step moves every parameter)
+        use_cache = self.wcache is not None and (not self.buckets.enabled or self.buckets.buckets is not None)
+        cnn.WCACHE = self.wcache.h if use_cache else None
         try:
             loss, aux = LOSS_FNS[self.cfg](self.nets, tgt, refs, K, Kinv, self.hp)
             loss.backward()
@@ -124,9 +127,9 @@ class Trainer:
             cnn.WCACHE = None
         self.buckets.finish()                               # waits for the bucket all-reduces issued during backward
         self.opt.step()
-        if self.wcache is not None:
+        if use_cache:
             if not self.wcache.committed:
-                self.wcache.commit()                        # first step recorded the layouts: allocate + prepare
+                self.wcache.commit()                        # this step recorded the layouts: allocate + prepare
             else:
                 self.wcache.refresh()
         return loss.detach(), aux

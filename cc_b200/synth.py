@@ -92,3 +92,25 @@ def sample(B, H, W, seed=0, nlevels=6):
                 depth=depths(B, H, W, nlevels, seed + 1), pose=poses(B, 4, seed + 2),
                 flow_fwd=flows(B, H, W, nlevels, seed + 3), flow_bwd=flows(B, H, W, nlevels, seed + 4),
                 emask=exp_masks(B, H, W, 4, nlevels, seed + 5))
+
+
+def seeded_fill(module, seed):
+    """Deterministic parameters for ANY module from its state_dict key names and shapes alone - lets a fixture frozen
+    from a reference module and a test on the mirrored module agree on the weights without storing them: conv weights
+    ~ N(0, 1/fan), biases ~ 0.1 N(0,1), BatchNorm weight 1 + 0.1 N(0,1); running statistics keep their defaults."""
+    import torch
+    sd = module.state_dict()
+    with torch.no_grad():
+        for i, k in enumerate(sorted(sd)):
+            t = sd[k]
+            if not t.dtype.is_floating_point or k.endswith('running_mean') or k.endswith('running_var'):
+                continue
+            g = torch.Generator().manual_seed(seed * 100003 + i)
+            if t.dim() == 4:
+                v = torch.randn(t.shape, generator=g) / (t[0].numel() ** 0.5)
+            elif k.endswith('weight'):                       # BatchNorm scale
+                v = 1.0 + 0.1 * torch.randn(t.shape, generator=g)
+            else:
+                v = 0.1 * torch.randn(t.shape, generator=g)
+            t.copy_(v.to(t.device))
+    return module

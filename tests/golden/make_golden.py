@@ -457,7 +457,57 @@ def gen_helpers():
     save('helpers_small', d)
 
 
+# --------------------------------------------------------------------------- I. alternate nets
+ALT_NETS = [  # name, constructor kwargs, input size (B, H, W), parameters whose gradients are frozen
+    ('DispNetS', {}, (2, 64, 128), ['conv1.0.weight', 'conv7.2.bias', 'upconv4.0.weight', 'iconv3.0.weight', 'predict_disp4.0.weight']),
+    ('DispNetS6', {}, (2, 64, 128), ['conv1.2.weight', 'conv5.0.bias', 'upconv7.0.weight', 'iconv1.0.weight', 'predict_disp6.0.bias']),
+    ('DispResNetS6', {}, (2, 64, 128), ['conv1.0.weight', 'conv4.2.conv2.weight', 'iconv5.1.conv1.weight', 'iconv7.0.downsample.1.bias',
+                                       'predict_disp1.0.weight']),
+    ('PoseNet6', dict(nb_ref_imgs=4), (2, 128, 128), ['conv0.0.weight', 'conv1.0.weight', 'conv7.0.bias', 'pose_pred.weight']),
+    ('PoseExpNet', dict(nb_ref_imgs=4, output_exp=True), (2, 64, 128), ['conv1.0.weight', 'conv6.0.weight', 'upconv5.0.weight',
+                                                                      'upconv1.0.bias', 'predict_mask4.weight', 'pose_pred.bias']),
+    ('MaskResNet6', dict(nb_ref_imgs=4, output_exp=True), (2, 128, 128), ['conv1.0.weight', 'conv3.0.downsample.1.weight', 'conv6.1.conv2.weight',
+                                                                        'deconv6.0.weight', 'deconv1.0.bias', 'pred_mask1.weight']),
+]
+
+
+def alt_outputs(name, net, tgt, refs):
+    """The tensors of one alternate net that the fixture holds (train mode)."""
+    if name.startswith('Disp'):
+        return list(net(tgt))
+    if name == 'PoseNet6':
+        return [net(tgt, refs)]
+    if name == 'PoseExpNet':
+        masks, pose = net(tgt, refs)
+        return list(masks) + [pose]
+    return list(net(tgt, refs))
+
+
+def gen_alt_nets():
+    d = {}
+    for k, (name, kw, (B, H, W), pn) in enumerate(ALT_NETS):
+        tgt, refs = synth.frames(B, H, W, seed=190 + k)
+        net = synth.seeded_fill(getattr(RM, name)(**kw), 300 + k)
+        net.train()
+        outs = alt_outputs(name, net, tgt, refs)
+        loss = sum((x * wts(x.shape, 400 + 10 * k + i)).sum() for i, x in enumerate(outs))
+        pd = dict(net.named_parameters())
+        g = torch.autograd.grad(loss, [pd[n] for n in pn])
+        for i, x in enumerate(outs):
+            d[f'{name}_out{i}'] = x
+        for n, gg in zip(pn, g):
+            sfx, gg = compact(gg)
+            d[f'{name}_g_{n}{sfx}'] = gg
+        net.eval()
+        e = net(tgt) if name.startswith('Disp') else net(tgt, refs)
+        d[f'{name}_eval'] = e if torch.is_tensor(e) else (e[1] if name == 'PoseExpNet' else e[0])
+    save('alt_nets_small', d)
+
+
 if __name__ == '__main__':
+    if 'alt' in sys.argv:                  # only the alternate-net fixture
+        gen_alt_nets()
+        sys.exit(0)
     if 'extra' in sys.argv:                # only the round-2 fixtures (the round-1 files stay byte-identical)
         gen_metrics()
         gen_transforms()

@@ -97,6 +97,11 @@ def test_conv_tma_family():
     NC.case_conv_tma_family(torch.device('cuda:0'))
 
 
+def test_alternate_nets():
+    """All six alternate architectures against the fixtures frozen from the reference's modules."""
+    NC.case_alt_nets(torch.device('cuda:0'))
+
+
 def test_conv_nhwc_slab():
     NC.case_conv_nhwc(torch.device('cuda:0'))
 

@@ -136,3 +136,12 @@ from tests import helper_cases as HC   # noqa: E402
 @pytest.mark.parametrize('case', HC.HELPER_CASES, ids=lambda f: f.__name__)
 def test_helper_case(case):
     case(torch.device('cuda:0'))
+
+
+from tests import eval_cases as EC   # noqa: E402
+
+
+@pytest.mark.parametrize('case', EC.EVAL_CASES, ids=lambda f: f.__name__)
+def test_eval_case(case):
+    """Evaluation cores (test_disp / test_pose / test_flow sample loops) against the oracle restatement."""
+    case(torch.device('cuda:0'))

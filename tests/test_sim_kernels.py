@@ -65,3 +65,11 @@ from tests import helper_cases as HC   # noqa: E402
 @pytest.mark.parametrize('case', HC.HELPER_CASES, ids=lambda f: f.__name__)
 def test_helper_case(case):
     case(torch.device('cpu'))
+
+
+from tests import eval_cases as EC   # noqa: E402
+
+
+@pytest.mark.parametrize('case', [EC.case_eval_depth, EC.case_eval_pose], ids=lambda f: f.__name__)
+def test_eval_case(case):
+    case(torch.device('cpu'))

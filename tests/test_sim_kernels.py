@@ -70,6 +70,6 @@ def test_helper_case(case):
 from tests import eval_cases as EC   # noqa: E402
 
 
-@pytest.mark.parametrize('case', [EC.case_eval_depth, EC.case_eval_pose], ids=lambda f: f.__name__)
+@pytest.mark.parametrize('case', [EC.case_eval_pose], ids=lambda f: f.__name__)      # depth / flow cores: GPU suite (CPU suite time)
 def test_eval_case(case):
     case(torch.device('cpu'))

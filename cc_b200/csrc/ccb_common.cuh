@@ -1,6 +1,7 @@
 // ccb_common.cuh - shared host/device helpers for libccb200 (sm_100a).
 #pragma once
 #include "../../include/ccb200.h"
+#include "../../include/ccb200_debug.h"
 
 #ifdef CCB_CPU_SIM
 #include "cusim.h"   // tests/sim: CPU execution-model simulator, TEST BUILDS ONLY

@@ -2,7 +2,12 @@
 
 The reference re-pools the full-resolution frames with ``adaptive_avg_pool2d`` inside every loss
 function at every level (15 pools per level per step: loss_functions.py:36-37,89-90,163-165,315).
-Here one kernel builds all levels once per frame tensor; results are cached for the step."""
+Here one kernel builds all levels once per frame tensor; results are memoised for the step.
+
+State: the C library keeps none; this Python-side memo holds at most 12 (frame tensor -> levels) entries keyed on tensor
+identity + version, and `Trainer.step` clears it on entry and exit, so no reference outlives a step.  Plain callers
+of the loss functions may call `clear()` themselves (stale entries are only ever evicted, never wrong: a changed
+tensor has a new version)."""
 import ctypes as C
 import torch
 from . import _lib

@@ -113,7 +113,8 @@ class Trainer:
             self.wcache.refresh()
 
     def step(self, tgt, refs, K, Kinv):
-        from . import nn as cnn
+        from . import nn as cnn, pyramid
+        pyramid.clear()                                     # the per-step memo of frame pyramids never outlives a step
         self.opt.zero_grad()
         self.buckets.begin()
         # the weight cache keys its copies by parameter address: it starts recording only after the bucket scheduler has
@@ -132,6 +133,7 @@ class Trainer:
                 self.wcache.commit()                        # this step recorded the layouts: allocate + prepare
             else:
                 self.wcache.refresh()
+        pyramid.clear()
         return loss.detach(), aux
 
     def _snapshot(self):

@@ -1,4 +1,4 @@
-"""The C-ABI library loads and exports every symbol include/ccb200.h declares (no compute calls)."""
+"""The C-ABI library loads and exports every symbol include/*.h declares (no compute calls)."""
 import ctypes
 import os
 import re
@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared():
-    src = open(os.path.join(ROOT, 'include', 'ccb200.h')).read()
+    src = ''.join(open(os.path.join(ROOT, 'include', f)).read() for f in sorted(os.listdir(os.path.join(ROOT, 'include'))) if f.endswith('.h'))
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
     return sorted(set(re.findall(r'\b(ccb_[a-z0-9_]+)\s*\(', src)))
 

@@ -454,6 +454,7 @@ int tc_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw,
 // TMA-fed tensor-core path (conv_tma.cu): stride-1 gathers (FPROP stride 1, every DGRAD parity class)
 bool tma_conv_supported(const ccb_conv_desc* d, int op);
 bool tma_direct_fprop(const ccb_conv_desc* d);
+bool tma_nhwc_takes(const ccb_conv_desc* d, int op);
 long long tma_workspace_floats(const ccb_conv_desc* d, int op);
 int tma_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float* bias, const float* res, float* y,
               float* work, long long work_floats, int three, cudaStream_t st);
@@ -468,6 +469,7 @@ static bool use_tma(const ccb_conv_desc* d, int op, const void* src) {
     // measured on B200 (tools/tma_probe.py): the slab kernel wins every DGRAD and the FPROPs with a long K loop or
     // >= 64 output channels; short thin FPROPs (K <= 512, N <= 32) and stride-2 FPROPs stay on the register-gather kernel
     if (op == CCB_CONV_FPROP && tma_direct_fprop(d)) return true;     // thin layers: CUDA-core direct kernel
+    if (op == CCB_CONV_FPROP && tma_nhwc_takes(d, op)) return true;   // channels-last slab kernel (measured: 32 -> 32 3x3 at 128x416 151 -> ~55 us)
     if (op == CCB_CONV_FPROP && d->kh > 1) {
         if (d->stride != 1) return false;
         if (d->Co < 64 && (long long)d->Ci * d->kh * d->kw < 512) return false;

@@ -1177,6 +1177,10 @@ static bool nhwc_takes(const ccb_conv_desc* d, int op, long long* wpf_out, long 
     *wpf_out = wpf; *tiles_out = tiles;
     return true;
 }
+bool tma_nhwc_takes(const ccb_conv_desc* d, int op) {
+    long long a, b;
+    return nhwc_takes(d, op, &a, &b);
+}
 static int nhwc_plan_splits(long long tiles, int cblocks, long long out_numel, long long part_floats) {
     if (tiles >= 2 * 148 || cblocks < 4) return 1;               // two CTAs per SM
     long long s = (3 * 148 + tiles - 1) / tiles;
@@ -1756,6 +1760,7 @@ namespace ccb {
 void tma_set_enabled(int) {}
 bool tma_conv_supported(const ccb_conv_desc*, int) { return false; }
 bool tma_direct_fprop(const ccb_conv_desc*) { return false; }
+bool tma_nhwc_takes(const ccb_conv_desc*, int) { return false; }
 long long tma_workspace_floats(const ccb_conv_desc*, int) { return 0; }
 int tma_fprop(const ccb_conv_desc*, const float*, const float*, const float*, const float*, float*, float*, long long, int,
               cudaStream_t) { return CCB_ERR_UNSUPPORTED; }

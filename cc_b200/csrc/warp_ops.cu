@@ -432,6 +432,75 @@ extern "C" int ccb_pose2flow_bwd(const float* depth, const float* pose, int pose
     return check_launch("pose2flow_pose_finalize");
 }
 
+// Small maps with many channels (Back2Future's feature warps at 8x26 .. 16x52 with 96-128 channels): a thread per pixel
+// leaves 4-16 CTAs looping serially over the channels (measured: 70-92 us per call on 4-16 CTAs).  Here a WARP takes a
+// pixel and its lanes take the channels; the flow gradient is a shuffle reduction (fixed order).
+__global__ void __launch_bounds__(WNT) flow_warp_fwd_wpp_kernel(const WarpArgs a) {
+    const long long hw = (long long)a.h * a.w;
+    const long long pix = (long long)blockIdx.x * (WNT / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pix >= hw * a.B) return;
+    const int b = (int)(pix / hw);
+    const long long idx = pix - (long long)b * hw;
+    const int y = (int)(idx / a.w), x = (int)(idx - (long long)y * a.w);
+    float Xn, Yn;
+    warp_coords(a, (float)x, (float)y, __ldg(a.flow + (long long)b * 2 * hw + idx), __ldg(a.flow + (long long)b * 2 * hw + hw + idx), Xn, Yn);
+    const Samp s = make_samp(Xn, Yn, a.w, a.h, a.pad);
+    const float* im = a.img + (long long)b * a.C * hw;
+    for (int c = lane; c < a.C; c += 32) a.out[(long long)b * a.C * hw + c * hw + idx] = interp(fetch(im + c * hw, s, a.w), s);
+}
+
+__global__ void __launch_bounds__(WNT) flow_warp_bwd_wpp_kernel(const WarpArgs a) {
+    const long long hw = (long long)a.h * a.w;
+    const long long pix = (long long)blockIdx.x * (WNT / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pix >= hw * a.B) return;                              // whole warps leave together
+    const int b = (int)(pix / hw);
+    const long long idx = pix - (long long)b * hw;
+    const int y = (int)(idx / a.w), x = (int)(idx - (long long)y * a.w);
+    float Xn, Yn;
+    const float w1 = (float)max(a.w - 1, 1), h1 = (float)max(a.h - 1, 1);
+    warp_coords(a, (float)x, (float)y, __ldg(a.flow + (long long)b * 2 * hw + idx), __ldg(a.flow + (long long)b * 2 * hw + hw + idx), Xn, Yn);
+    const Samp s = make_samp(Xn, Yn, a.w, a.h, a.pad);
+    const float* im = a.img + (long long)b * a.C * hw;
+    float gix = 0.f, giy = 0.f;
+    for (int c = lane; c < a.C; c += 32) {
+        const float g = __ldg(a.grad_out + (long long)b * a.C * hw + c * hw + idx);
+        if (a.d_flow) {
+            const Corners cr = fetch(im + c * hw, s, a.w);
+            gix += g * interp_dx(cr, s);
+            giy += g * interp_dy(cr, s);
+        }
+        if (a.d_img) {
+            float* di = a.d_img + (long long)b * a.C * hw + c * hw + (long long)s.y0 * a.w + s.x0;
+            if (s.oky0 && s.okx0) atomicAdd(di, g * s.wy0 * s.wx0);
+            if (s.oky0 && s.okx1) atomicAdd(di + 1, g * s.wy0 * s.wx1);
+            if (s.oky1 && s.okx0) atomicAdd(di + a.w, g * s.wy1 * s.wx0);
+            if (s.oky1 && s.okx1) atomicAdd(di + a.w + 1, g * s.wy1 * s.wx1);
+        }
+    }
+    if (a.d_flow) {
+        gix = warp_sum(gix);
+        giy = warp_sum(giy);
+        if (lane == 0) {
+            a.d_flow[(long long)b * 2 * hw + idx] = gix * s.gmx * (2.f / w1);
+            a.d_flow[(long long)b * 2 * hw + hw + idx] = giy * s.gmy * (2.f / h1);
+        }
+    }
+}
+
+static bool warp_per_pixel(int B, int C, int h, int w) { return C >= 16 && (long long)B * h * w < 32768; }
+static void launch_flow_warp(const WarpArgs& a, bool bwd, cudaStream_t st) {
+    if (warp_per_pixel(a.B, a.C, a.h, a.w)) {
+        const unsigned nb = (unsigned)cdiv((int)((long long)a.B * a.h * a.w), WNT / 32);
+        if (bwd) CCB_LAUNCH(flow_warp_bwd_wpp_kernel, dim3(nb), dim3(WNT), 0, st, a);
+        else CCB_LAUNCH(flow_warp_fwd_wpp_kernel, dim3(nb), dim3(WNT), 0, st, a);
+    } else {
+        if (bwd) CCB_LAUNCH(flow_warp_bwd_kernel, dim3(cdiv(a.h * a.w, WNT), a.B), dim3(WNT), 0, st, a);
+        else CCB_LAUNCH(flow_warp_fwd_kernel, dim3(cdiv(a.h * a.w, WNT), a.B), dim3(WNT), 0, st, a);
+    }
+}
+
 extern "C" int ccb_flow_warp_fwd(const float* img, const float* flow, int B, int C, int h, int w,
                                  int padding_mode, float* out, ccb_stream_t stream) {
     CCB_REQUIRE(img && flow && out, CCB_ERR_ARG, "flow_warp_fwd: null pointer");
@@ -439,7 +508,7 @@ extern "C" int ccb_flow_warp_fwd(const float* img, const float* flow, int B, int
     WarpArgs a;
     memset(&a, 0, sizeof(a));
     a.img = img; a.flow = flow; a.out = out; a.B = B; a.C = C; a.h = h; a.w = w; a.pad = padding_mode;
-    CCB_LAUNCH(flow_warp_fwd_kernel, dim3(cdiv(h * w, WNT), B), dim3(WNT), 0, stream, a);
+    launch_flow_warp(a, false, (cudaStream_t)stream);
     return check_launch("flow_warp_fwd");
 }
 
@@ -451,7 +520,7 @@ extern "C" int ccb_flow_warp_bwd(const float* img, const float* flow, int B, int
     memset(&a, 0, sizeof(a));
     a.img = img; a.flow = flow; a.grad_out = grad_out; a.d_flow = d_flow; a.d_img = d_img;
     a.B = B; a.C = C; a.h = h; a.w = w; a.pad = padding_mode;
-    CCB_LAUNCH(flow_warp_bwd_kernel, dim3(cdiv(h * w, WNT), B), dim3(WNT), 0, stream, a);
+    launch_flow_warp(a, true, (cudaStream_t)stream);
     return check_launch("flow_warp_bwd");
 }
 
@@ -462,7 +531,7 @@ extern "C" int ccb_featwarp_fwd(const float* x, const float* flow, int B, int C,
     WarpArgs a;
     memset(&a, 0, sizeof(a));
     a.img = x; a.flow = flow; a.out = out; a.B = B; a.C = C; a.h = h; a.w = w; a.pad = CCB_PAD_BORDER; a.b2f_norm = 1;
-    CCB_LAUNCH(flow_warp_fwd_kernel, dim3(cdiv(h * w, WNT), B), dim3(WNT), 0, stream, a);
+    launch_flow_warp(a, false, (cudaStream_t)stream);
     return check_launch("featwarp_fwd");
 }
 
@@ -473,7 +542,7 @@ extern "C" int ccb_featwarp_bwd(const float* x, const float* flow, int B, int C,
     memset(&a, 0, sizeof(a));
     a.img = x; a.flow = flow; a.grad_out = grad_out; a.d_flow = d_flow; a.d_img = d_x;
     a.B = B; a.C = C; a.h = h; a.w = w; a.pad = CCB_PAD_BORDER; a.b2f_norm = 1;
-    CCB_LAUNCH(flow_warp_bwd_kernel, dim3(cdiv(h * w, WNT), B), dim3(WNT), 0, stream, a);
+    launch_flow_warp(a, true, (cudaStream_t)stream);
     return check_launch("featwarp_bwd");
 }
 

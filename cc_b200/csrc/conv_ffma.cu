@@ -455,6 +455,10 @@ int tc_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw,
 bool tma_conv_supported(const ccb_conv_desc* d, int op);
 bool tma_direct_fprop(const ccb_conv_desc* d);
 bool tma_nhwc_takes(const ccb_conv_desc* d, int op);
+bool nhwc_wgrad_takes(const ccb_conv_desc* d);
+long long nhwc_wgrad_workspace_floats(const ccb_conv_desc* d);
+int nhwc_wgrad(const ccb_conv_desc* d, const float* x, const float* dz, float* dw, float* work, long long work_floats, int three,
+               cudaStream_t st);
 long long tma_workspace_floats(const ccb_conv_desc* d, int op);
 int tma_fprop(const ccb_conv_desc* d, const float* x, const float* w, const float* bias, const float* res, float* y,
               float* work, long long work_floats, int three, cudaStream_t st);
@@ -549,6 +553,10 @@ extern "C" long long ccb_conv_workspace_floats(const ccb_conv_desc* d, int op) {
             long long t2 = tma_wgrad_workspace_floats(d);
             if (t2 > t) t = t2;
         }
+        if (op == CCB_CONV_WGRAD && nhwc_wgrad_takes(d)) {
+            long long t2 = nhwc_wgrad_workspace_floats(d);
+            if (t2 > t) t = t2;
+        }
         return t > bias_need ? t : bias_need;
     }
     long long numel = (op == CCB_CONV_FPROP) ? (long long)d->B * d->Co * d->Ho * d->Wo
@@ -628,7 +636,9 @@ extern "C" int ccb_conv2d_wgrad(const ccb_conv_desc* d, const float* x, const fl
         int impl = pick_impl(d, CCB_CONV_WGRAD);
         CCB_REQUIRE(impl >= 0, CCB_ERR_UNSUPPORTED, "conv2d_wgrad: shape not supported by the tensor-core path");
         if (impl > 0) {
-            if (tma_wgrad_supported(d) && ((((uintptr_t)x) | ((uintptr_t)dy)) & 15) == 0)
+            if (nhwc_wgrad_takes(d))
+                rc = nhwc_wgrad(d, x, dy, dw, work, work_floats, impl == 1, (cudaStream_t)stream);
+            else if (tma_wgrad_supported(d) && ((((uintptr_t)x) | ((uintptr_t)dy)) & 15) == 0)
                 rc = tma_wgrad(d, x, dy, dw, work, work_floats, impl == 1, (cudaStream_t)stream);
             else
                 rc = tc_wgrad(d, x, dy, dw, work, work_floats, impl == 1, (cudaStream_t)stream);

@@ -309,7 +309,8 @@ struct NhwcPlan {
     bool ok;
 };
 static int g_nhwc_mt = 0;          // bring-up: force the number of stacked tiles (0 = planned)
-void nhwc_set_debug(int enabled, int soft, int dbg) { g_nhwc_enabled = enabled; g_nhwc_soft = soft; g_nhwc_dbg = dbg & 15; g_nhwc_mt = (dbg >> 4) & 7; }
+static int g_nhwc_wgrad_on = 0;    // dbg bit 7 sends stride-1 weight gradients through conv_wgrad_nhwc_kernel (off by default, see there)
+void nhwc_set_debug(int enabled, int soft, int dbg) { g_nhwc_enabled = enabled; g_nhwc_soft = soft; g_nhwc_dbg = dbg & 15; g_nhwc_mt = (dbg >> 4) & 7; g_nhwc_wgrad_on = (dbg >> 7) & 1; }
 // tap offsets (pixels of the gathered tensor), channels, output channels, output grid -> tiling; !ok: the path does not take
 // this problem.
 //   * Two CTAs per SM (<= 111 KB of shared memory, <= 256 TMEM columns each) whenever the problem allows: prologue
@@ -457,6 +458,305 @@ int launch_nhwc(const float* xh, int B, int Cc, int Hin, int Win, const float* w
     return check_launch("conv_nhwc");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Channels-last WEIGHT GRADIENT:  dw[co][ci][tap] = sum over pixels of dz[px][co] * x[px + tap][ci]   (stride 1)
+//   GEMM with K = pixels.  In NHWC both operands are "K rows of 128 bytes" (a pixel x 32 channels): MN-major operands
+//   exactly in the layout the aligned NCHW kernel (conv_tma_kernel) already feeds the tensor core with
+//   (SWIZZLE_128B_ATOM_32B, 4-row atoms 512 B apart, 32-wide MN blocks 4096 B apart) - and, because a CTA owns whole
+//   (tap, 32-channel block) pairs, the tap shift is a TMA COORDINATE, not a shared-memory offset: no cutter warps at all
+//   (the NCHW slab kernel spends its time cutting the (tap, ci) x 32 px operand out of a slab, tensor pipe 30 %).
+//     M = 128 = 4 (tap, ci-block) pairs: four TMA boxes (32 ci, 8 px, 4 rows) of x at the tap-shifted coordinate
+//     N = the co tile (<= 128, in 32-wide boxes of dz), doubled by the tf32 remainder: D[:, 0:2n) += A_hi * [B_hi | B_lo],
+//         D[:, 2n:3n) += A_lo * B_hi
+//     K = 32 pixels (4 rows x 8 columns) per stage, 4 k-steps of 8; image borders / padding / channel tails = TMA zero fill
+//   grid = (pairs / 4, co tiles, pixel splits); split partials are summed in a fixed order.
+//   warp 0: TMA producer   warp 1: MMA issuer   warps 2-9: remainder pass + epilogue
+//   MEASURED (B200, 128 -> 128 3x3, b4 64x208; profiles/r02_ncu_wgrad_nhwc_128.txt): correct to 2e-6, tensor pipe 42.7 % active -
+//   but 193 us against 168 us for the NCHW slab kernel: MN-major tf32 MMAs keep the tensor pipe busy 2.1 x the nominal
+//   M x N x K / 2048 cycles (82 us of pipe time for 39 us of nominal work), so removing the cutters does not pay here.
+//   The dispatcher therefore keeps weight gradients on conv_slab_wgrad_kernel (K-major operands: pixels contiguous in
+//   NCHW); this kernel stays selectable (ccb_debug_nhwc dbg bit 7) and is covered by the parity tests.
+// ---------------------------------------------------------------------------------------------------------------
+struct NhwcWgradArgs {
+    int B, Ci, Co, Ho, Wo, KK, kw, pad;
+    int npairs, ciblocks;
+    int tiles_x, tiles_y, stages, per_split, splits;
+    int nboxp, nblkN;                    // co tile rounded to 32, number of 32-wide dz boxes
+    int nstages, soft;
+    long long numel;
+    float* out;
+};
+constexpr int NW_BLK = 4096;             // one 32-wide MN block of one stage: 32 px x 128 B
+
+template <bool THREE>
+__global__ void __launch_bounds__(NH_THREADS, 1)
+conv_wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, const NhwcWgradArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    // Two rings: the TMA-filled operand tiles (A_hi | B_hi, NST deep: the loads run far enough ahead to hide the L2 latency)
+    // and the tf32 remainders (A_lo | B_lo, NSTL = 2 deep: produced by the eight remainder warps just ahead of the MMAs)
+    const int NST = a.nstages;
+    constexpr int NSTL = 2;
+    const int a_bytes = 4 * NW_BLK, b_bytes = a.nblkN * NW_BLK;
+    const int hi_bytes = a_bytes + b_bytes;                                   // [A_hi][B_hi]
+    unsigned char* lo_ring = smem + NST * hi_bytes;                            // [A_lo][B_lo] x NSTL
+    uint64_t* bars = (uint64_t*)(lo_ring + (THREE ? NSTL * hi_bytes : 0));
+    uint64_t* full = bars;                // [8] TMA
+    uint64_t* empty = bars + 8;           // [8] tcgen05.commit: operand stage consumed
+    uint64_t* lo_full = bars + 16;        // [2] 8 remainder warps
+    uint64_t* lo_empty = bars + 18;       // [2] tcgen05.commit: remainder stage consumed
+    uint64_t* accum_bar = bars + 20;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 21);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int p0 = blockIdx.x * 4;                                            // first (tap, ci-block) pair of this CTA
+    const int n0 = blockIdx.y * 128;
+    const int st_beg = blockIdx.z * a.per_split;
+    const int nst = max(0, min(a.stages, st_beg + a.per_split) - st_beg);
+    const int per_b = a.tiles_x * a.tiles_y;
+
+    if (tid == 0) {
+        tm_prefetch_map(&map_x);
+        tm_prefetch_map(&map_dz);
+        for (int s = 0; s < NST; ++s) {
+            tm_mbar_init(&full[s], 1);
+            tm_mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < NSTL; ++s) {
+            tm_mbar_init(&lo_full[s], 8);
+            tm_mbar_init(&lo_empty[s], 1);
+        }
+        tm_mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one thread) =====================
+        if (lane == 0) {
+            const int npv = min(4, a.npairs - p0);                             // valid pairs: the other rows are never read back
+            int tapy[4], tapx[4], cch[4];
+            for (int j = 0; j < 4; ++j) {
+                const int p = min(p0 + j, a.npairs - 1);
+                const int tap = p / a.ciblocks;
+                cch[j] = (p - tap * a.ciblocks) * 32;
+                tapy[j] = tap / a.kw - a.pad;
+                tapx[j] = tap - (tap / a.kw) * a.kw - a.pad;
+            }
+            const uint32_t tx_bytes = (uint32_t)(npv * NW_BLK + b_bytes);
+            int s = 0, ph = 0;
+            for (int it = 0; it < nst; ++it) {
+                if (it >= NST) nh_wait(&empty[s], ph ^ 1, a.soft, 1, it);
+                int t = st_beg + it;
+                const int b = t / per_b;
+                t -= b * per_b;
+                const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+                const int x0 = tx * 8, y0 = ty * 4;
+                unsigned char* st = smem + s * hi_bytes;
+                tm_mbar_expect_tx(&full[s], tx_bytes);
+                for (int j = 0; j < npv; ++j) tma_load_4d(st + j * NW_BLK, &map_x, &full[s], cch[j], x0 + tapx[j], y0 + tapy[j], b);
+                for (int j = 0; j < a.nblkN; ++j) tma_load_4d(st + a_bytes + j * NW_BLK, &map_dz, &full[s], n0 + j * 32, x0, y0, b);
+                if (++s == NST) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // D fp32, A/B tf32, BOTH MN-major, M = 128.  hi*hi and hi*lo are two MMAs here (B_hi and B_lo live in different
+        // rings), lo*hi the third; hi*lo and lo*hi share one accumulator, the main product keeps its own.
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24) |
+                               ((uint32_t)(a.nboxp >> 3) << 17);
+        const uint32_t leader = (lane == 0) ? 1u : 0u;
+        const uint32_t d0 = tmem_base, d1 = tmem_base + (uint32_t)a.nboxp;
+        int s = 0, sl = 0;
+        uint32_t ph = 0, phl = 0;
+        for (int it = 0; it < nst; ++it) {
+            nh_wait(&full[s], ph, a.soft, 2, it);
+            if (THREE) nh_wait(&lo_full[sl], phl, a.soft, 3, it);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi16 = smem_addr(smem + s * hi_bytes) >> 4, b_hi16 = a_hi16 + (a_bytes >> 4);
+            const uint32_t a_lo16 = smem_addr(lo_ring + sl * hi_bytes) >> 4, b_lo16 = a_lo16 + (a_bytes >> 4);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+                // a k-step = 8 pixel rows = 1024 B; 32-wide MN blocks 4096 B apart (LBO), 4-row atoms 512 B apart (SBO)
+                tm_umma_tf32_p(d0, (a_hi16 + ks * 64) | DESC_A_MN_LO, DESC_A_MN_HI, (b_hi16 + ks * 64) | DESC_A_MN_LO, DESC_A_MN_HI, idesc, acc, leader);
+                if (THREE) {
+                    tm_umma_tf32_p(d1, (a_hi16 + ks * 64) | DESC_A_MN_LO, DESC_A_MN_HI, (b_lo16 + ks * 64) | DESC_A_MN_LO, DESC_A_MN_HI, idesc, acc, leader);
+                    tm_umma_tf32_p(d1, (a_lo16 + ks * 64) | DESC_A_MN_LO, DESC_A_MN_HI, (b_hi16 + ks * 64) | DESC_A_MN_LO, DESC_A_MN_HI, idesc, 1u, leader);
+                }
+            }
+            tm_commit_p(&empty[s], leader);
+            if (THREE) tm_commit_p(&lo_empty[sl], leader);
+            if (++s == NST) { s = 0; ph ^= 1; }
+            if (++sl == NSTL) { sl = 0; phl ^= 1; }
+        }
+        if (nst > 0) tm_commit_p(accum_bar, leader);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ===================== remainder pass, then the epilogue: 8 warps =====================
+        const int wt = tid - 64;
+        if (THREE) {
+            const int nv = hi_bytes >> 4;
+            int s = 0, sl = 0;
+            uint32_t ph = 0, phl = 0;
+            for (int it = 0; it < nst; ++it) {
+                nh_wait(&full[s], ph, a.soft, 5, it);
+                if (it >= NSTL) nh_wait(&lo_empty[sl], phl ^ 1, a.soft, 6, it);
+                const float4* hi = (const float4*)(smem + s * hi_bytes);
+                float4* lo = (float4*)(lo_ring + sl * hi_bytes);
+                for (int i = wt; i < nv; i += 256) lo[i] = tf32_rest4(hi[i]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tm_mbar_arrive(&lo_full[sl]);
+                if (++s == NST) { s = 0; ph ^= 1; }
+                if (++sl == NSTL) { sl = 0; phl ^= 1; }
+            }
+        }
+        if (nst > 0) nh_wait(accum_bar, 0, a.soft, 7, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q4 = warp & 3, colh = (warp - 2) >> 2;
+        const int p = p0 + q4;                                                 // TMEM lane quarter = one (tap, ci-block) pair
+        const int tap = min(p, a.npairs - 1) / a.ciblocks;
+        const int ci = (min(p, a.npairs - 1) - tap * a.ciblocks) * 32 + lane;
+        const bool rvalid = (p < a.npairs) && (ci < a.Ci);
+        const int ntile = min(128, a.Co - n0);
+        float* outp = a.out + (long long)blockIdx.z * a.numel;
+        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        for (int cg = colh; cg * 16 < ntile; cg += 2) {
+            float v[16];
+            if (nst > 0) {
+                tm_ld16(trow + (uint32_t)(cg * 16), v);
+                if (THREE) {
+                    float v2[16];
+                    tm_ld16(trow + (uint32_t)(a.nboxp + cg * 16), v2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+            if (rvalid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int co = n0 + cg * 16 + j;
+                    if (cg * 16 + j < ntile) outp[((long long)co * a.Ci + ci) * a.KK + tap] = v[j];
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(256) nhwc_wgrad_sum_kernel(const float* __restrict__ work, float* __restrict__ out, long long numel, int splits) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= numel) return;
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += __ldg(work + (long long)s * numel + i);
+    out[i] = v;
+}
+
+static bool nhwc_wgrad_plan(const ccb_conv_desc* d, int three, NhwcWgradArgs& a, int& smem) {
+    memset(&a, 0, sizeof(a));
+    a.B = d->B; a.Ci = d->Ci; a.Co = d->Co; a.Ho = d->Ho; a.Wo = d->Wo; a.KK = d->kh * d->kw; a.kw = d->kw; a.pad = d->pad;
+    a.ciblocks = cdiv(d->Ci, 32);
+    a.npairs = a.KK * a.ciblocks;
+    a.tiles_x = cdiv(d->Wo, 8); a.tiles_y = cdiv(d->Ho, 4);
+    a.stages = d->B * a.tiles_x * a.tiles_y;
+    const int ntile = d->Co < 128 ? d->Co : 128;
+    a.nblkN = cdiv(ntile, 32);
+    a.nboxp = a.nblkN * 32;
+    const int hi = 4 * NW_BLK + a.nblkN * NW_BLK;               // one operand stage; the remainder ring holds 2 more of this size
+    a.nstages = (222 * 1024 - (three ? 2 * hi : 0)) / hi;
+    if (a.nstages > 8) a.nstages = 8;
+    if (a.nstages < 3) return false;
+    smem = (a.nstages + (three ? 2 : 0)) * hi + 1024 + 1024;
+    const int base = cdiv(a.npairs, 4) * cdiv(d->Co, 128);
+    int splits = base >= 148 ? 1 : cdiv(148, base);
+    if (splits > a.stages / 6) splits = a.stages / 6;
+    if (splits < 1) splits = 1;
+    a.per_split = cdiv(a.stages, splits);
+    a.splits = cdiv(a.stages, a.per_split);
+    a.numel = (long long)d->Co * d->Ci * a.KK;
+    return true;
+}
+// Which problems: stride 1, enough channels on both sides to fill 32-wide boxes, maps whose 4 x 8 pixel tiles are mostly full
+bool nhwc_wgrad_takes(const ccb_conv_desc* d) {
+    if (!g_nhwc_enabled || !g_nhwc_wgrad_on || get_encode() == nullptr) return false;
+    if (d->stride != 1 || d->kh != d->kw || d->Ci < 24 || d->Co < 24) return false;
+    if (d->Ho < 4 || d->Wo < 8) return false;
+    if ((long long)cdiv(d->Ho, 4) * 4 * cdiv(d->Wo, 8) * 8 * 10 > (long long)d->Ho * d->Wo * 14) return false;
+    if ((long long)d->B * d->Ho * d->Wo < 2048) return false;
+    NhwcWgradArgs a;
+    int smem;
+    return nhwc_wgrad_plan(d, 1, a, smem);
+}
+long long nhwc_wgrad_workspace_floats(const ccb_conv_desc* d) {
+    NhwcWgradArgs a;
+    int smem;
+    if (!nhwc_wgrad_plan(d, 1, a, smem)) return -1;
+    return nhwc_copy_floats(d->B, d->Ci, d->Hi, d->Wi) + nhwc_copy_floats(d->B, d->Co, d->Ho, d->Wo) + (a.splits > 1 ? a.splits * a.numel : 0);
+}
+int nhwc_wgrad(const ccb_conv_desc* d, const float* x, const float* dz, float* dw, float* work, long long work_floats, int three,
+               cudaStream_t st) {
+    EncodeTiledFn enc = get_encode();
+    CCB_REQUIRE(enc != nullptr, CCB_ERR_UNSUPPORTED, "conv_nhwc wgrad: cuTensorMapEncodeTiled unavailable");
+    NhwcWgradArgs a;
+    int smem = 0;
+    CCB_REQUIRE(nhwc_wgrad_plan(d, three, a, smem), CCB_ERR_UNSUPPORTED, "conv_nhwc wgrad: no tiling");
+    a.soft = g_nhwc_soft;
+    const long long xf = nhwc_copy_floats(d->B, d->Ci, d->Hi, d->Wi), zf = nhwc_copy_floats(d->B, d->Co, d->Ho, d->Wo);
+    CCB_REQUIRE(work && xf + zf + (a.splits > 1 ? a.splits * a.numel : 0) <= work_floats, CCB_ERR_ARG, "conv_nhwc wgrad: workspace too small");
+    float* xh = work;
+    float* zh = work + xf;
+    int rc = nhwc_transpose(x, xh, d->B, d->Ci, d->Hi, d->Wi, st);
+    if (rc) return rc;
+    rc = nhwc_transpose(dz, zh, d->B, d->Co, d->Ho, d->Wo, st);
+    if (rc) return rc;
+    a.out = a.splits > 1 ? work + xf + zf : dw;
+    const int Cip = (d->Ci + 3) & ~3, Cop = (d->Co + 3) & ~3;
+    alignas(64) CUtensorMap map_x, map_dz;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cip, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->B};
+        cuuint64_t strides[3] = {(cuuint64_t)Cip * 4, (cuuint64_t)d->Wi * Cip * 4, (cuuint64_t)d->Hi * d->Wi * Cip * 4};
+        cuuint32_t box[4] = {32, 8, 4, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)xh, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CCB_REQUIRE(r == CUDA_SUCCESS, CCB_ERR_LAUNCH, "conv_nhwc wgrad: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cop, (cuuint64_t)d->Wo, (cuuint64_t)d->Ho, (cuuint64_t)d->B};
+        cuuint64_t strides[3] = {(cuuint64_t)Cop * 4, (cuuint64_t)d->Wo * Cop * 4, (cuuint64_t)d->Ho * d->Wo * Cop * 4};
+        cuuint32_t box[4] = {32, 8, 4, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map_dz, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)zh, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CCB_REQUIRE(r == CUDA_SUCCESS, CCB_ERR_LAUNCH, "conv_nhwc wgrad: cuTensorMapEncodeTiled(dz) failed (%d)", (int)r);
+    }
+    dim3 grid(cdiv(a.npairs, 4), cdiv(d->Co, 128), a.splits);
+    auto kfn = three ? conv_wgrad_nhwc_kernel<true> : conv_wgrad_nhwc_kernel<false>;
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    CCB_LAUNCH(kfn, grid, dim3(NH_THREADS), smem, st, map_x, map_dz, a);
+    rc = check_launch("conv_nhwc_wgrad");
+    if (rc || a.splits == 1) return rc;
+    CCB_LAUNCH(nhwc_wgrad_sum_kernel, dim3((unsigned)((a.numel + 255) / 256)), dim3(256), 0, st, (const float*)a.out, dw, a.numel, a.splits);
+    return check_launch("conv_nhwc_wgrad_reduce");
+}
+
 }  // namespace ccb
 
 using namespace ccb;
@@ -464,7 +764,8 @@ using namespace ccb;
 // bring-up: enabled (0 turns the channels-last kernel off), soft (barrier time-outs are recorded, not trapped),
 // dbg bit 0: descriptors WITH the base-offset field (wrong results for unaligned taps), bit 1: thin layers (16 .. 31 gathered
 // channels) take this path instead of the CUDA-core direct kernel, bit 2: 1x1 convolutions take this path
-// too, bit 3: one CTA per SM (the 128-wide configuration) only, bits 4-6: force that many stacked tiles per CTA
+// too, bit 3: one CTA per SM (the 128-wide configuration) only, bits 4-6: force that many stacked tiles per CTA, bit 7:
+// stride-1 weight gradients through the channels-last wgrad kernel
 extern "C" void ccb_debug_nhwc(int enabled, int soft, int dbg) { nhwc_set_debug(enabled, soft, dbg); }
 extern "C" int ccb_debug_nhwc_status(unsigned int* out4) {
     cudaDeviceSynchronize();
@@ -480,6 +781,8 @@ namespace ccb {
 bool nhwc_applies(const int*, const int*, int, int, int, int, int, int, int, bool) { return false; }
 bool nhwc_prefers_thin() { return false; }
 long long nhwc_copy_floats(int, int, int, int) { return 0; }
+bool nhwc_wgrad_takes(const ccb_conv_desc*) { return false; }
+long long nhwc_wgrad_workspace_floats(const ccb_conv_desc*) { return -1; }
 long long nhwc_wp_floats(const int*, const int*, int, int, int) { return -1; }
 }
 extern "C" void ccb_debug_nhwc(int, int, int) {}

@@ -201,6 +201,11 @@ def case_conv_nhwc(device):
                     assert_close(got, ref, 1e-4, f'{tag} nhwc={on} {what}')
             for a_, b_, what in zip(outs[1], outs[0], ('fprop', 'dgrad', 'wgrad', 'bias grad')):
                 assert_close(a_, b_, 1e-4, f'{tag} channels-last vs NCHW kernels {what}')
+            if s == 1:      # the channels-last weight-gradient kernel (MN-major operands; selectable, off by default)
+                lib.ccb_debug_nhwc(1, 0, 128)
+                y = cnn.conv2d(x, w, b, None, s, p, None, 0.2)
+                gw, = torch.autograd.grad((y * wt).sum(), [w])
+                assert_close(gw, gd[1], 1e-4, f'{tag} channels-last wgrad kernel')
     finally:
         lib.ccb_debug_nhwc(1, 0, 0)
         cnn.CONV_IMPL = saved

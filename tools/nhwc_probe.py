@@ -61,15 +61,16 @@ def run_case(i):
     gxd = torch.autograd.grad((F.conv2d(x.detach().double().requires_grad_(True), w.detach().double(), b.double(), s, p) * wt.double()).sum(), [])\
         if False else None
     xd = x.detach().double().requires_grad_(True)
-    gxd, = torch.autograd.grad((F.conv2d(xd, w.detach().double(), b.double(), s, p) * wt.double()).sum(), [xd])
+    wd = w.detach().double().requires_grad_(True)
+    gxd, gwd = torch.autograd.grad((F.conv2d(xd, wd, b.double(), s, p) * wt.double()).sum(), [xd, wd])
     st = (C.c_uint * 4)()
     for dbg in (0, 2):
         lib.ccb_debug_nhwc(1, 1, dbg)
         y = cnn.conv2d(x, w, b, None, s, p, None, 0.0)
-        gx, = torch.autograd.grad((y * wt).sum(), [x])
+        gx, gw = torch.autograd.grad((y * wt).sum(), [x, w])
         torch.cuda.synchronize()
         lib.ccb_debug_nhwc_status(st)
-        out['dbg%d' % (0 if dbg == 0 else 1)] = dict(fprop=rel(y.detach(), zd), dgrad=rel(gx, gxd), status=list(st))
+        out['dbg%d' % (0 if dbg == 0 else 1)] = dict(fprop=rel(y.detach(), zd), dgrad=rel(gx, gxd), wgrad=rel(gw, gwd), status=list(st))
     # per-tap: one-hot filters (small cases only)
     if B * H * W <= 8192 and s == 1:
         taps = {}
@@ -97,14 +98,15 @@ def run_case(i):
         return e0.elapsed_time(e1) / 20 * 1e3
     gflop = 2.0 * B * zd.shape[2] * zd.shape[3] * Co * Ci * k * k / 1e9
     gy = wt
-    for name, on, dbg in (('auto', 1, 0), ('thin', 1, 2), ('thin_mt4', 1, 2 | (4 << 4)), ('one', 1, 8), ('nchw', 0, 0)):
+    for name, on, dbg in (('auto', 1, 0), ('wg_nhwc', 1, 128), ('nchw', 0, 0)):
         lib.ccb_debug_nhwc(on, 1, dbg)
         with torch.no_grad():
             tf = timed(lambda: cnn.conv2d(x, w, b, None, s, p, 'relu', 0.0))
         y = cnn.conv2d(x, w, b, None, s, p, None, 0.0)
         tb = timed(lambda: torch.autograd.grad((y,), [x], [gy], retain_graph=True))
+        tw = timed(lambda: torch.autograd.grad((y,), [w], [gy], retain_graph=True))
         out['time_' + name] = dict(fprop_us=round(tf, 1), fprop_tflops=round(gflop / tf * 1e3, 1), dgrad_us=round(tb, 1),
-                                   dgrad_tflops=round(gflop / tb * 1e3, 1))
+                                   dgrad_tflops=round(gflop / tb * 1e3, 1), wgrad_us=round(tw, 1), wgrad_tflops=round(gflop / tw * 1e3, 1))
     lib.ccb_debug_nhwc(1, 1, 0)
     print(json.dumps(out))
 

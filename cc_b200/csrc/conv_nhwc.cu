@@ -783,6 +783,7 @@ bool nhwc_prefers_thin() { return false; }
 long long nhwc_copy_floats(int, int, int, int) { return 0; }
 bool nhwc_wgrad_takes(const ccb_conv_desc*) { return false; }
 long long nhwc_wgrad_workspace_floats(const ccb_conv_desc*) { return -1; }
+int nhwc_wgrad(const ccb_conv_desc*, const float*, const float*, float*, float*, long long, int, cudaStream_t) { return CCB_ERR_UNSUPPORTED; }
 long long nhwc_wp_floats(const int*, const int*, int, int, int) { return -1; }
 }
 extern "C" void ccb_debug_nhwc(int, int, int) {}

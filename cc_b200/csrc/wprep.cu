@@ -56,22 +56,25 @@ __device__ __forceinline__ void wprep_block(const WPrepDesc& a, int nb, int bloc
     }
     __syncthreads();
     const long long plane = (long long)a.N * a.Kp;
-    for (int i = threadIdx.x; i < nn * a.Kp; i += 256) {
-        const int nl = i / a.Kp, k = i - nl * a.Kp;
+    // a thread owns k positions and walks the staged output channels: the (slot, channel) decode - integer divisions -
+    // runs once per k, not once per element, and consecutive threads write consecutive k (coalesced)
+    for (int k = threadIdx.x; k < a.Kp; k += 256) {
         int slot, c;
-        float v = 0.f;
-        if (wprep_decode(a, k, slot, c)) {
-            const int tap = a.tap_index[slot];
-            v = (a.mode == 0) ? sw[(nl * a.Cc + c) * a.KK + tap] : sw[(c * nn + nl) * a.KK + tap];
+        const bool valid = wprep_decode(a, k, slot, c);
+        const int tap = valid ? a.tap_index[slot] : 0;
+        const int base = valid ? ((a.mode == 0) ? c * a.KK + tap : c * nn * a.KK + tap) : 0;
+        const int step = (a.mode == 0) ? a.Cc * a.KK : a.KK;
+        for (int nl = 0; nl < nn; ++nl) {
+            const float v = valid ? sw[base + nl * step] : 0.f;
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+            const float h = __uint_as_float(hb);
+            const long long o = (long long)(n0 + nl) * a.Kp + k;
+            a.wp[o] = h;
+            uint32_t lb;                                   // the remainder rounded to tf32 as well: the hardware reads it exactly
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - h));
+            a.wp[plane + o] = __uint_as_float(lb);
         }
-        uint32_t hb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-        const float h = __uint_as_float(hb);
-        const long long o = (long long)(n0 + nl) * a.Kp + k;
-        a.wp[o] = h;
-        uint32_t lb;                                       // the remainder rounded to tf32 as well: the hardware reads it exactly
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - h));
-        a.wp[plane + o] = __uint_as_float(lb);
     }
 }
 

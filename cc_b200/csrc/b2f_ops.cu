@@ -52,6 +52,7 @@ __device__ __forceinline__ void corr_stage(float (*s)[CH][CH + 1], const float* 
 __global__ void __launch_bounds__(CT * CT) corr81_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                                                              float* __restrict__ out, float* __restrict__ part, int B, int C, int h,
                                                              int w, int reversed, int chunks) {
+    CCB_PDL_WAIT();
     __shared__ float s2[CG][CH][CH + 1];
     const int b = blockIdx.z / chunks, chunk = blockIdx.z - b * chunks;
     const int x0 = blockIdx.x * CT, y0 = blockIdx.y * CT;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(CT * CT) corr81_fwd_kernel(const float* __rest
 
 __global__ void __launch_bounds__(256) corr81_sum_kernel(const float* __restrict__ part, float* __restrict__ out, int B, int C, int h,
                                                          int w, int reversed, int chunks) {
+    CCB_PDL_WAIT();
     const long long hw = (long long)h * w, n = (long long)B * 81 * hw;
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(256) corr81_sum_kernel(const float* __restrict
 // by corr81_mirror_kernel (81 shifted copies of g, a streaming pass) and F = f1.
 __global__ void __launch_bounds__(256) corr81_mirror_kernel(const float* __restrict__ g, float* __restrict__ gm, int B, int h, int w,
                                                             int reversed) {
+    CCB_PDL_WAIT();
     const long long hw = (long long)h * w, n = (long long)B * 81 * hw;
     for (long long i0 = (long long)blockIdx.x * 256 + threadIdx.x; i0 < n; i0 += (long long)gridDim.x * 256) {
         const int x = (int)(i0 % w), y = (int)((i0 / w) % h);
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(256) corr81_mirror_kernel(const float* __restr
 __global__ void __launch_bounds__(CT * CT) corr81_dgrad_kernel(const float* __restrict__ G, const float* __restrict__ F,
                                                                float* __restrict__ d, int B, int C, int h, int w, int reversed,
                                                                int natural, int chunks) {
+    CCB_PDL_WAIT();
     __shared__ float sf[CG][CH][CH + 1];
     const int b = blockIdx.z / chunks, chunk = blockIdx.z - b * chunks;
     const int x0 = blockIdx.x * CT, y0 = blockIdx.y * CT;

@@ -11,16 +11,43 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
-#define CCB_LAUNCH(kern, grid, block, smem, stream, ...)                           \
-    do {                                                                            \
-        ++ccb::g_launches;                                                          \
-        kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);     \
+// Every kernel is launched with programmatic stream serialisation (PDL) and starts with CCB_PDL_WAIT(): a kernel's
+// launch + block scheduling then overlaps the tail of its predecessor (inside the step's CUDA graph: programmatic edges),
+// and griddepcontrol.wait holds it before its first global-memory access until the predecessor has completed and flushed -
+// same results, ~1900 launch gaps per step shorter.  CCB_PDL=0 in the environment turns the attribute off.
+#define CCB_LAUNCH(kern_, grid_, block_, smem_, stream_, ...)                                     \
+    do {                                                                                           \
+        ++ccb::g_launches;                                                                         \
+        cudaLaunchConfig_t cfg_ = {};                                                              \
+        cfg_.gridDim = (grid_);                                                                    \
+        cfg_.blockDim = (block_);                                                                  \
+        cfg_.dynamicSmemBytes = (size_t)(smem_);                                                   \
+        cfg_.stream = (cudaStream_t)(stream_);                                                     \
+        cudaLaunchAttribute at_[1];                                                                \
+        at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                            \
+        at_[0].val.programmaticStreamSerializationAllowed = ccb::pdl_enabled();                    \
+        cfg_.attrs = at_;                                                                          \
+        cfg_.numAttrs = 1;                                                                         \
+        cudaLaunchKernelEx(&cfg_, kern_, __VA_ARGS__);                                             \
+    } while (0)
+// CCB_PDL_TRIGGER: let the SUCCESSOR's blocks be scheduled as soon as every block of this grid has started (they park at their
+// own CCB_PDL_SYNC; no block of this grid is left unscheduled by then, so nothing can starve).  CCB_PDL_SYNC: wait for the
+// predecessor's completion + memory flush; must precede the first access to global data.  CCB_PDL_WAIT: both, at the top of
+// a kernel.  The tensor-core kernels trigger at the top and sync AFTER their prologue (barrier init, TMEM allocation), which
+// therefore overlaps the predecessor's tail.
+#define CCB_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define CCB_PDL_SYNC() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define CCB_PDL_WAIT()      \
+    do {                    \
+        CCB_PDL_SYNC();     \
+        CCB_PDL_TRIGGER();  \
     } while (0)
 #define CCB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
 namespace ccb {
 extern long long g_launches;   // kernels launched through the library by this process (bench.py gpu_launches)
+int pdl_enabled();             // common.cu: 1 unless CCB_PDL=0
 }
 
 namespace ccb {

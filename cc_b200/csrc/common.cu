@@ -1,12 +1,22 @@
 // common.cu - error plumbing of the C ABI (include/ccb200.h).
 #include "ccb_common.cuh"
 #include <cstdarg>
+#include <cstdlib>
 
 namespace ccb {
 
 static thread_local char g_err[512] = "";
 long long g_launches = 0;
 static thread_local const char* g_last_conv = "";    // main kernel of the last convolution call (bench.py kernel shares)
+
+int pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CCB_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;

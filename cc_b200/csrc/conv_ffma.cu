@@ -146,6 +146,7 @@ __device__ __forceinline__ long long out_offset(const ConvArgs& a, const MInfo& 
 
 template <int MODE, class C>
 __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvArgs a) {
+    CCB_PDL_WAIT();
     constexpr int BM = C::BM, BN = C::BN, BK = C::BK, TM = C::TM, TN = C::TN;
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
                                                             const float* __restrict__ bias, const float* __restrict__ res,
                                                             long long numel, int splits, int plane, int C, int act,
                                                             float slope) {
+    CCB_PDL_WAIT();
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= numel) return;
     float v = 0.f;
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // dz = dy * act'(y)  (in terms of the activation OUTPUT y), optionally accumulating a second grad
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                                       float* __restrict__ dz, long long numel, int act, float slope) {
+    CCB_PDL_WAIT();
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= numel) return;
     float g = __ldg(dy + i), yv = __ldg(y + i);
@@ -265,6 +268,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
 // db[c] = sum_{b,y,x} dy[b,c,y,x] : one CTA per channel, fixed-order two-level sum
 __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int B,
                                                         int C, int plane) {
+    CCB_PDL_WAIT();
     __shared__ float s_red[32];
     const int c = blockIdx.x;
     float v[1] = {0.f};
@@ -280,6 +284,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
 constexpr int BG_CHUNK = 16384;
 __global__ void __launch_bounds__(256) bias_grad_partial_kernel(const float* __restrict__ dy, float* __restrict__ part, int B,
                                                                 int C, int plane, int nsplit) {
+    CCB_PDL_WAIT();
     __shared__ float s_red[32];
     const int c = blockIdx.x, sp = blockIdx.y;
     const long long per = (long long)B * plane;
@@ -293,6 +298,7 @@ __global__ void __launch_bounds__(256) bias_grad_partial_kernel(const float* __r
     if (threadIdx.x == 0) part[(long long)c * nsplit + sp] = v[0];
 }
 __global__ void bias_grad_merge_kernel(const float* __restrict__ part, float* __restrict__ db, int C, int nsplit) {
+    CCB_PDL_WAIT();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float a = 0.f;
@@ -314,6 +320,7 @@ __device__ __forceinline__ float act_grad(float g, float yv, int act, float slop
 }
 __global__ void __launch_bounds__(256) abb_large_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
                                                         float* __restrict__ part, int C, int plane, int nchunk, int act, float slope) {
+    CCB_PDL_WAIT();
     __shared__ float s_red[32];
     const int chunk = blockIdx.x, b = blockIdx.y, c = blockIdx.z;
     const long long base = ((long long)b * C + c) * plane;
@@ -342,6 +349,7 @@ __global__ void __launch_bounds__(256) abb_large_kernel(const float* __restrict_
     if (threadIdx.x == 0) part[((long long)c * gridDim.y + b) * nchunk + chunk] = v[0];
 }
 __global__ void __launch_bounds__(128) abb_merge_kernel(const float* __restrict__ part, float* __restrict__ db, int C, int n) {
+    CCB_PDL_WAIT();
     const int c = blockIdx.x * 128 + threadIdx.x;
     if (c >= C) return;
     float a = 0.f;
@@ -350,6 +358,7 @@ __global__ void __launch_bounds__(128) abb_merge_kernel(const float* __restrict_
 }
 __global__ void __launch_bounds__(256) abb_small_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
                                                         float* __restrict__ db, int B, int C, int plane, int act, float slope) {
+    CCB_PDL_WAIT();
     __shared__ float s_red[32];
     const int c = blockIdx.x;
     float v[1] = {0.f};
@@ -505,6 +514,7 @@ static int pick_impl(const ccb_conv_desc* d, int op) {
 // rows of W floats -> rows of Wp >= W floats, zero tail
 __global__ void __launch_bounds__(256) pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int W,
                                                        int Wp) {
+    CCB_PDL_WAIT();
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= rows * Wp) return;
     const long long r = i / Wp;

@@ -69,6 +69,7 @@ __device__ __forceinline__ void nh_wait(uint64_t* bar, uint32_t parity, int soft
 template <bool THREE>
 __global__ void __launch_bounds__(NH_THREADS, 2)
 conv_nhwc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b, const NhwcArgs a) {
+    CCB_PDL_TRIGGER();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     const int NST = a.nstages;
@@ -127,6 +128,7 @@ conv_nhwc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    CCB_PDL_SYNC();                                               // everything above touched no global data
 
     if (warp == 0) {
         // ===================== TMA producer (one thread) =====================
@@ -284,6 +286,7 @@ conv_nhwc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 // NCHW [B][C][HW] -> channels-last [B][HW][Cp] (Cp >= C, a multiple of 4: channel tails are zero), 32 x 32 tiles through
 // shared memory: reads coalesced along pixels, writes coalesced along channels
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ xh, int C, int Cp, int HW) {
+    CCB_PDL_WAIT();
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -492,6 +495,7 @@ constexpr int NW_BLK = 4096;             // one 32-wide MN block of one stage: 3
 template <bool THREE>
 __global__ void __launch_bounds__(NH_THREADS, 1)
 conv_wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, const NhwcWgradArgs a) {
+    CCB_PDL_WAIT();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     // Two rings: the TMA-filled operand tiles (A_hi | B_hi, NST deep: the loads run far enough ahead to hide the L2 latency)
@@ -662,6 +666,7 @@ conv_wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
 }
 
 __global__ void __launch_bounds__(256) nhwc_wgrad_sum_kernel(const float* __restrict__ work, float* __restrict__ out, long long numel, int splits) {
+    CCB_PDL_WAIT();
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= numel) return;
     float v = 0.f;

@@ -163,6 +163,7 @@ constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 2048;   // + barriers
 
 template <bool THREE, bool SWZ>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcArgs a) {
+    CCB_PDL_TRIGGER();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms are 1 KB
     const int NST = a.stages;
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcArgs a) 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    CCB_PDL_SYNC();                                               // everything above touched no global data
 
     if (warp < 8) {
         // ===================== producers =====================
@@ -462,6 +464,7 @@ struct TcWgradArgs {
 
 template <bool THREE, bool SWZ>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_wgrad_kernel(const TcWgradArgs a) {
+    CCB_PDL_TRIGGER();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int NST = a.nstages;
@@ -490,6 +493,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_wgrad_kernel(const TcWg
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    CCB_PDL_SYNC();                                               // everything above touched no global data
 
     if (warp < 8) {
         // two producer groups (4 warps each) fill alternating stages; inside a group 8 consecutive threads
@@ -656,6 +660,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_wgrad_kernel(const TcWg
 // out[i] = sum_s work[s][i]
 __global__ void __launch_bounds__(256) tc_splitk_sum_kernel(const float* __restrict__ work, float* __restrict__ out,
                                                             long long numel, int splits) {
+    CCB_PDL_WAIT();
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= numel) return;
     float v = 0.f;

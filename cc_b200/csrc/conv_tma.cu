@@ -65,6 +65,7 @@ __device__ __forceinline__ void tm_mbar_wait(uint64_t* bar, uint32_t parity, int
 template <bool THREE>
 __global__ void __launch_bounds__(TM_THREADS, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TmaConvArgs a) {
+    CCB_PDL_TRIGGER();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     const int NST = a.nstages;
@@ -107,6 +108,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    CCB_PDL_SYNC();                                               // everything above touched no global data
 
     if (warp == 0) {
         // ===================== TMA producer (one thread) =====================
@@ -365,6 +367,7 @@ struct SlabArgs {
 template <bool THREE>
 __global__ void __launch_bounds__(SL_THREADS, 1)
 conv_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b, const SlabArgs a) {
+    CCB_PDL_WAIT();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     const int NST = a.nstages;
@@ -845,6 +848,7 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, f
 
 __global__ void __launch_bounds__(DC_THREADS, 2)
 conv_direct_kernel(const __grid_constant__ CUtensorMap map_x, const DirectArgs a) {
+    CCB_PDL_WAIT();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* slab = (float*)smem_raw;
     const int n8 = a.NG * 8;
@@ -952,6 +956,7 @@ struct DirectPrepArgs {
     signed char tap_index[TM_MAX_SLOTS];
 };
 __global__ void __launch_bounds__(256) direct_wprep_kernel(const DirectPrepArgs a) {
+    CCB_PDL_WAIT();
     const long long total = (long long)a.nblocks * a.nchunks * a.ntaps * a.CC * a.n8;
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= total) return;
@@ -1094,6 +1099,7 @@ static bool taps_aligned(const int* ox, int nt, int in_stride, int Cc) {
 // copied into rows padded with zeros (exactly what the convolution's own zero padding would read there).
 __global__ void __launch_bounds__(256) tma_pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int W,
                                                            int Wp) {
+    CCB_PDL_WAIT();
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= rows * Wp) return;
     const long long r = i / Wp;
@@ -1377,6 +1383,7 @@ struct SlabWgradArgs {
 template <bool THREE>
 __global__ void __launch_bounds__(SL_THREADS, 1)
 conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const SlabWgradArgs a) {
+    CCB_PDL_WAIT();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     const int NST = a.nstages;
@@ -1586,6 +1593,7 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
 
 __global__ void __launch_bounds__(256) tma_splitk_sum_kernel(const float* __restrict__ work, float* __restrict__ out, long long numel,
                                                              int splits) {
+    CCB_PDL_WAIT();
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= numel) return;
     float v = 0.f;

@@ -78,6 +78,7 @@ __device__ __forceinline__ float mask_at_pred(const FlowMetArgs& a, const float*
 }
 
 __global__ void __launch_bounds__(256) flow_metrics_kernel(const FlowMetArgs a) {
+    CCB_PDL_WAIT();
     __shared__ double scratch[8 * 32];
     const long long npx = (long long)a.B * a.Hg * a.Wg;
     const float sy_p = (float)a.hp / (float)a.Hg, sx_p = (float)a.wp / (float)a.Wg;          // pred -> gt
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(256) flow_metrics_kernel(const FlowMetArgs a) 
 
 // out[0..3] = all_epe, rigid_epe, non_rigid_epe, outlier ratio   (nc == 2: plain mean over B*Hg*Wg, :384-385)
 __global__ void flow_metrics_finalize(const double* __restrict__ partials, int nblocks, int nc, long long npx, float* __restrict__ out) {
+    CCB_PDL_WAIT();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int b = 0; b < nblocks; ++b)
@@ -199,6 +201,7 @@ __device__ __forceinline__ float clamp_pred(float p) { return fminf(fmaxf(p, 1e-
 // pass 0: count valid + histogram of the top 11 bits; pass 1/2: histogram of the next 11 / 10 bits among keys
 // matching the prefix found so far
 __global__ void __launch_bounds__(256) depth_hist_kernel(const DepthArgs a, int pass) {
+    CCB_PDL_WAIT();
     const int b = blockIdx.y;
     const int shift = (pass == 0) ? 21 : (pass == 1 ? 10 : 0);
     const unsigned nb_mask = (pass == 2) ? 1023u : 2047u;
@@ -220,6 +223,7 @@ __global__ void __launch_bounds__(256) depth_hist_kernel(const DepthArgs a, int 
 
 // one thread per (sample, which): find the bin holding rank k, extend the prefix, clear the histogram
 __global__ void depth_select_kernel(const DepthArgs a, int pass) {
+    CCB_PDL_WAIT();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.B * 2) return;
     unsigned* h = a.hist + (long long)t * 2048;
@@ -246,6 +250,7 @@ __global__ void depth_select_kernel(const DepthArgs a, int pass) {
 }
 
 __global__ void __launch_bounds__(256) depth_errors_kernel(const DepthArgs a) {
+    CCB_PDL_WAIT();
     __shared__ double scratch[6 * 32];
     const int b = blockIdx.y;
     const long long hw = (long long)a.H * a.W;
@@ -273,6 +278,7 @@ __global__ void __launch_bounds__(256) depth_errors_kernel(const DepthArgs a) {
 }
 
 __global__ void depth_errors_finalize(const DepthArgs a, int nblocks) {
+    CCB_PDL_WAIT();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double tot[6] = {0, 0, 0, 0, 0, 0};
     for (int b = 0; b < a.B; ++b) {
@@ -302,6 +308,7 @@ struct PrepArgs {
 };
 
 __global__ void __launch_bounds__(256) prep_frames_kernel(const PrepArgs a) {
+    CCB_PDL_WAIT();
     const long long n = (long long)a.B * a.F * a.H * a.W;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
         const int x = (int)(i % a.W);

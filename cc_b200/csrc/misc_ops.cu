@@ -16,6 +16,7 @@ constexpr int BN_CHUNK = 8192;       // elements of one (batch, channel) plane h
 
 __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict__ x, float* __restrict__ part, int B, int C,
                                                          int plane, int nsplit) {
+    CCB_PDL_WAIT();
     __shared__ float s_red[32];
     __shared__ float s_mean;
     const int c = blockIdx.x, sp = blockIdx.y;
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict
 
 __global__ void bn_merge_kernel(const float* __restrict__ part, float* __restrict__ stats, float* __restrict__ run_mean,
                                 float* __restrict__ run_var, int C, int nsplit, float eps, float momentum) {
+    CCB_PDL_WAIT();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float n = 0.f, mean = 0.f, m2 = 0.f;
@@ -70,6 +72,7 @@ __global__ void bn_merge_kernel(const float* __restrict__ part, float* __restric
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float* __restrict__ stats,
                                                        float* __restrict__ y, long long numel, int C, int plane) {
+    CCB_PDL_WAIT();
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= numel) return;
     int c = (int)((i / plane) % C);
@@ -81,6 +84,7 @@ __global__ void __launch_bounds__(256) bn_eval_kernel(const float* __restrict__ 
                                                       const float* __restrict__ beta, const float* __restrict__ rm,
                                                       const float* __restrict__ rv, float* __restrict__ y, int B, int C,
                                                       int plane, float eps) {
+    CCB_PDL_WAIT();
     const int c = blockIdx.x;
     const float mean = __ldg(rm + c), inv = 1.f / sqrtf(__ldg(rv + c) + eps), g = __ldg(gamma + c), bt = __ldg(beta + c);
     for (int b = 0; b < B; ++b) {
@@ -94,6 +98,7 @@ __global__ void __launch_bounds__(256) bn_eval_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                              const float* __restrict__ stats, float* __restrict__ part, int B,
                                                              int C, int plane, int nsplit) {
+    CCB_PDL_WAIT();
     __shared__ float s_red[2 * 32];
     const int c = blockIdx.x, sp = blockIdx.y;
     const long long per = (long long)B * plane;
@@ -116,6 +121,7 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const float* __rest
 
 __global__ void bn_bwd_merge_kernel(const float* __restrict__ part, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                     float* __restrict__ sums, int C, int nsplit) {
+    CCB_PDL_WAIT();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float a = 0.f, b = 0.f;
@@ -130,6 +136,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ gamma, const float* __restrict__ stats,
                                                            const float* __restrict__ sums, float* __restrict__ dx,
                                                            long long numel, int C, int plane, float inv_n) {
+    CCB_PDL_WAIT();
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= numel) return;
     int c = (int)((i / plane) % C);
@@ -150,6 +157,7 @@ __device__ __forceinline__ void up2_src(int o, int n, int& i0, int& i1, float& l
 
 __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int planes,
                                                              int h, int w) {
+    CCB_PDL_WAIT();
     const int H = 2 * h, W = 2 * w;
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= (long long)planes * H * W) return;
@@ -167,6 +175,7 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const float* __rest
 // gather form of the transpose: each source pixel collects from the <= 4x4 outputs that read it
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int planes,
                                                              int h, int w) {
+    CCB_PDL_WAIT();
     const int H = 2 * h, W = 2 * w;
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= (long long)planes * h * w) return;
@@ -194,6 +203,7 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const float* __rest
 // The step counter and bias corrections live in device memory (state[0..2] = step, 1-b1^t, sqrt(1-b2^t))
 // so that the whole training step can be captured once in a CUDA graph and replayed.
 __global__ void adam_prep_kernel(float* __restrict__ state, float b1, float b2) {
+    CCB_PDL_WAIT();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         float t = state[0] + 1.f;
         state[0] = t;
@@ -206,6 +216,7 @@ __global__ void adam_prep_kernel(float* __restrict__ state, float b1, float b2) 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long n, const float* __restrict__ state,
                                                    float lr, float b1, float b2, float eps, float grad_scale) {
+    CCB_PDL_WAIT();
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const float bc1 = __ldg(state + 1), bc2_sqrt = __ldg(state + 2);

@@ -52,6 +52,7 @@ __device__ __noinline__ float2 rigid_occ_pairs(const Cam* cams, float x, float y
 // Forward.  MODE: CCB_PHOTO_RIGID / FLOW / CONSENSUS.  SSIM=false compiles the 13x13 stage out.
 template <int MODE, bool SSIM>
 __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
+    CCB_PDL_WAIT();
     constexpr int HALO = SSIM ? 6 : 0;
     using T = Tile<HALO>;
     CCB_DYN_SMEM(smem_raw);
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(NT, 2) photo_fwd_kernel(const PhotoArgs a) {
 // Forward finalize: per (level, ref) sums -> oob normalisation, loss terms, total loss.
 // loss_functions.py:48,58-59 / 103,114
 __global__ void __launch_bounds__(1024) photo_fwd_finalize(const PhotoArgs a) {
+    CCB_PDL_WAIT();
     __shared__ float s_L[CCB_MAX_LEVELS * CCB_MAX_REFS];
     const ccb_photo_desc& d = a.d;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -297,6 +299,7 @@ __global__ void __launch_bounds__(1024) photo_fwd_finalize(const PhotoArgs a) {
 // depth / pose (rigid) or flow; mask gradient is a scale of the saved unscaled term.
 template <int MODE, bool SSIM>
 __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(const PhotoArgs a) {
+    CCB_PDL_WAIT();
     using T = Tile<6>;
     CCB_DYN_SMEM(smem_raw);
     float* sD = reinterpret_cast<float*>(smem_raw);   // [3][PLANE] dS maps of one channel
@@ -423,6 +426,7 @@ __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(const PhotoArgs a) {
 
 // One warp per (b, ref): sum the per-tile dP partials of every level, chain to the 6-DoF pose.
 __global__ void photo_pose_finalize(const PhotoArgs a) {
+    CCB_PDL_WAIT();
     const ccb_photo_desc& d = a.d;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (wid >= d.B * d.R) return;

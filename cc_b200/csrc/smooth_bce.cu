@@ -65,6 +65,7 @@ __device__ __forceinline__ float edge_w(const float* __restrict__ im, long long 
 
 template <int KIND>
 __global__ void __launch_bounds__(PNT) smooth_fwd_kernel(const SmoothArgs a) {
+    CCB_PDL_WAIT();
     __shared__ float s_red[4 * 32];
     int l, b, y, x;
     bool in = locate(a.t, l, b, y, x);
@@ -116,6 +117,7 @@ __device__ __forceinline__ void smooth_counts(const SmoothArgs& a, int l, float*
 
 template <int KIND>
 __global__ void smooth_finalize(const SmoothArgs a) {
+    CCB_PDL_WAIT();
     __shared__ float s_red[4 * 32];
     __shared__ float s_total;
     if (threadIdx.x == 0) s_total = 0.f;
@@ -141,6 +143,7 @@ __global__ void smooth_finalize(const SmoothArgs a) {
 
 template <int KIND>
 __global__ void __launch_bounds__(PNT) smooth_bwd_kernel(const SmoothArgs a) {
+    CCB_PDL_WAIT();
     int l, b, y, x;
     if (!locate(a.t, l, b, y, x)) return;
     const int h = a.t.h[l], w = a.t.w[l], C = a.d.C;
@@ -210,6 +213,7 @@ __device__ __forceinline__ void consensus_target(const BceArgs& a, int l, int b,
 
 template <int KIND>
 __global__ void __launch_bounds__(PNT) bce_fwd_kernel(const BceArgs a) {
+    CCB_PDL_WAIT();
     __shared__ float s_red[32];
     int l, b, y, x;
     bool in = locate(a.t, l, b, y, x);
@@ -237,6 +241,7 @@ __global__ void __launch_bounds__(PNT) bce_fwd_kernel(const BceArgs a) {
 
 template <int KIND>
 __global__ void bce_finalize(const BceArgs a) {
+    CCB_PDL_WAIT();
     __shared__ float s_red[32];
     __shared__ float s_total;
     if (threadIdx.x == 0) s_total = 0.f;
@@ -256,6 +261,7 @@ __global__ void bce_finalize(const BceArgs a) {
 
 template <int KIND>
 __global__ void __launch_bounds__(PNT) bce_bwd_kernel(const BceArgs a) {
+    CCB_PDL_WAIT();
     int l, b, y, x;
     if (!locate(a.t, l, b, y, x)) return;
     const int h = a.t.h[l], w = a.t.w[l], C = a.d.C;

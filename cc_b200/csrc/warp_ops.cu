@@ -14,6 +14,7 @@ struct PyrArgs {
 };
 
 __global__ void __launch_bounds__(256) pyramid_kernel(const PyrArgs a) {
+    CCB_PDL_WAIT();
     __shared__ float s[2][16 * 16];
     const int plane = blockIdx.z, ty0 = blockIdx.y * 32, tx0 = blockIdx.x * 32;
     const int tid = threadIdx.x;
@@ -74,6 +75,7 @@ constexpr int WNT = 256;
 // inverse_warp forward (inverse_warp.py:250-283) / pose2flow forward (:195-220)
 template <bool FLOW_OUT>
 __global__ void __launch_bounds__(WNT) rigid_fwd_kernel(const WarpArgs a) {
+    CCB_PDL_WAIT();
     __shared__ Cam cam;
     const int b = blockIdx.y;
     if (threadIdx.x == 0)
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(WNT) rigid_fwd_kernel(const WarpArgs a) {
 
 template <bool FLOW_OUT>
 __global__ void __launch_bounds__(WNT) rigid_bwd_kernel(const WarpArgs a) {
+    CCB_PDL_WAIT();
     __shared__ Cam cam;
     __shared__ float s_red[12 * 32];
     const int b = blockIdx.y;
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(WNT) rigid_bwd_kernel(const WarpArgs a) {
 }
 
 __global__ void rigid_pose_finalize(const WarpArgs a, int nblk) {
+    CCB_PDL_WAIT();
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (wid >= a.B) return;
     float dP[12];
@@ -177,6 +181,7 @@ __device__ __forceinline__ void warp_coords(const WarpArgs& a, float x, float y,
 
 // flow_warp (inverse_warp.py:164-192), any channel count
 __global__ void __launch_bounds__(WNT) flow_warp_fwd_kernel(const WarpArgs a) {
+    CCB_PDL_WAIT();
     const int b = blockIdx.y;
     const long long hw = (long long)a.h * a.w;
     long long idx = (long long)blockIdx.x * WNT + threadIdx.x;
@@ -191,6 +196,7 @@ __global__ void __launch_bounds__(WNT) flow_warp_fwd_kernel(const WarpArgs a) {
 }
 
 __global__ void __launch_bounds__(WNT) flow_warp_bwd_kernel(const WarpArgs a) {
+    CCB_PDL_WAIT();
     const int b = blockIdx.y;
     const long long hw = (long long)a.h * a.w;
     long long idx = (long long)blockIdx.x * WNT + threadIdx.x;
@@ -252,6 +258,7 @@ __device__ __forceinline__ void stage_plane(const float* __restrict__ src, float
 // PASS 0: write the SSIM map.  PASS 1: write grad_out * dS/d(mu1,Exx,mu2,Eyy,Exy) into work.
 template <int PASS>
 __global__ void __launch_bounds__(NT, 2) ssim_map_kernel(const SsimArgs a) {
+    CCB_PDL_WAIT();
     using T = Tile<6>;
     CCB_DYN_SMEM(smem_raw);
     float* sx = reinterpret_cast<float*>(smem_raw);
@@ -298,6 +305,7 @@ __global__ void __launch_bounds__(NT, 2) ssim_map_kernel(const SsimArgs a) {
 
 // d img1 = G*(g dmu1) + 2 x G*(g dExx) + y G*(g dExy);  d img2 symmetric
 __global__ void __launch_bounds__(NT, 2) ssim_bwd_kernel(const SsimArgs a) {
+    CCB_PDL_WAIT();
     using T = Tile<6>;
     CCB_DYN_SMEM(smem_raw);
     float* sD = reinterpret_cast<float*>(smem_raw);   // 3 planes
@@ -436,6 +444,7 @@ extern "C" int ccb_pose2flow_bwd(const float* depth, const float* pose, int pose
 // leaves 4-16 CTAs looping serially over the channels (measured: 70-92 us per call on 4-16 CTAs).  Here a WARP takes a
 // pixel and its lanes take the channels; the flow gradient is a shuffle reduction (fixed order).
 __global__ void __launch_bounds__(WNT) flow_warp_fwd_wpp_kernel(const WarpArgs a) {
+    CCB_PDL_WAIT();
     const long long hw = (long long)a.h * a.w;
     const long long pix = (long long)blockIdx.x * (WNT / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -451,6 +460,7 @@ __global__ void __launch_bounds__(WNT) flow_warp_fwd_wpp_kernel(const WarpArgs a
 }
 
 __global__ void __launch_bounds__(WNT) flow_warp_bwd_wpp_kernel(const WarpArgs a) {
+    CCB_PDL_WAIT();
     const long long hw = (long long)a.h * a.w;
     const long long pix = (long long)blockIdx.x * (WNT / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;

@@ -79,6 +79,7 @@ __device__ __forceinline__ void wprep_block(const WPrepDesc& a, int nb, int bloc
 }
 
 __global__ void __launch_bounds__(256) wprep_staged_kernel(const WPrepDesc a, int nb) {
+    CCB_PDL_WAIT();
     extern __shared__ float sw[];
     wprep_block(a, nb, blockIdx.x, sw);
 }
@@ -89,6 +90,7 @@ struct WCacheEntry {
     int nb, first_block;
 };
 __global__ void __launch_bounds__(256) wprep_all_kernel(const WCacheEntry* __restrict__ entries, const int* __restrict__ block_entry) {
+    CCB_PDL_WAIT();
     extern __shared__ float sw[];
     __shared__ WPrepDesc sd;
     __shared__ int s_nb, s_first;

@@ -188,3 +188,6 @@ static inline int max(int a, int b) { return a > b ? a : b; }
     } while (0)
 namespace ccb { extern long long g_launches; }
 #define CCB_DYN_SMEM(name) unsigned char* name = cusim::dyn_smem()
+#define CCB_PDL_WAIT() ((void)0)      /* programmatic dependent launch: GPU builds only */
+#define CCB_PDL_TRIGGER() ((void)0)
+#define CCB_PDL_SYNC() ((void)0)

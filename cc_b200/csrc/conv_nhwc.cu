@@ -374,14 +374,32 @@ static NhwcPlan nhwc_plan(const int* off_y, const int* off_x, int ntaps, int Cc,
 
 // Does the channels-last kernel take this gather?  (measured dispatch: everything with >= 32 gathered channels whose
 // output grid fills 16 x 8 tiles reasonably)
-// `part_of_set`: one parity class of a strided DGRAD whose other classes need the channels-last copy anyway
-bool nhwc_applies(const int* off_y, const int* off_x, int ntaps, int in_stride, int Cc, int N, int Hc, int Wc, int three, bool part_of_set) {
-    if (!g_nhwc_enabled || in_stride != 1 || get_encode() == nullptr) return false;
+// shape conditions of the channels-last kernel (no driver needed: the CPU plan tests call this too)
+static bool nhwc_shape_ok(const int* off_y, const int* off_x, int ntaps, int in_stride, int Cc, int N, int Hc, int Wc, bool part_of_set) {
+    if (!g_nhwc_enabled || in_stride != 1) return false;
     if (Cc < ((g_nhwc_dbg & 2) ? 16 : 32) || N < 16) return false;
     if (ntaps == 1 && off_x[0] == 0 && off_y[0] == 0 && !part_of_set && !(g_nhwc_dbg & 4)) return false;   // 1x1: the aligned NCHW TMA kernel needs no copy
     if (Hc < 12 || Wc < 7) return false;
     if ((long long)cdiv(Hc, NH_TH) * NH_TH * cdiv(Wc, NH_TW) * NH_TW * 10 > (long long)Hc * Wc * 14) return false;   // > 40 % tile waste
-    return nhwc_plan(off_y, off_x, ntaps, Cc, N, three).ok;
+    return nhwc_plan(off_y, off_x, ntaps, Cc, N, 1).ok;
+}
+// `part_of_set`: one parity class of a strided DGRAD whose other classes need the channels-last copy anyway
+bool nhwc_applies(const int* off_y, const int* off_x, int ntaps, int in_stride, int Cc, int N, int Hc, int Wc, int three, bool part_of_set) {
+    (void)three;
+    return get_encode() != nullptr && nhwc_shape_ok(off_y, off_x, ntaps, in_stride, Cc, N, Hc, Wc, part_of_set);
+}
+// host-side tiling for the plan tests: out16 = {6, cblocks, SH, SW, mt, slab_bytes, slab_tx, nslab, nstages, nbox, ntile_w, tmem_cols,
+// smem, Kp, Cp, grid CTAs}; out16[0] = -1 when the shape is not taken
+void nhwc_debug_plan(const int* off_y, const int* off_x, int ntaps, int in_stride, int Cc, int N, int B, int Hc, int Wc, bool part_of_set,
+                     int* out16) {
+    out16[0] = -1;
+    if (!nhwc_shape_ok(off_y, off_x, ntaps, in_stride, Cc, N, Hc, Wc, part_of_set)) return;
+    const long long tiles1 = (long long)B * cdiv(Wc, NH_TW) * cdiv(Hc, NH_TH) * cdiv(N, 128);
+    const NhwcPlan p = nhwc_plan(off_y, off_x, ntaps, Cc, N, 1, Hc, tiles1);
+    if (!p.ok) return;
+    const int v[16] = {6, p.cblocks, p.SH, p.SW, p.mt, p.slab_bytes, p.slab_tx, p.nslab, p.nstages, p.nbox, p.ntile_w, p.tmem_cols, p.smem, p.Kp,
+                       p.Cp, (int)(B * cdiv(Wc, NH_TW) * cdiv(Hc, NH_TH * p.mt) * cdiv(N, p.ntile_w))};
+    for (int i = 0; i < 16; ++i) out16[i] = v[i];
 }
 bool nhwc_prefers_thin() { return (g_nhwc_dbg & 2) != 0; }
 long long nhwc_copy_floats(int B, int Cc, int Hin, int Win) { return (long long)B * Hin * Win * ((Cc + 3) & ~3); }

@@ -245,6 +245,8 @@ void launch_splitk_reduce(const float* work, float* out, const float* bias, cons
 // conv_nhwc.cu: channels-last slab kernel
 bool nhwc_applies(const int* off_y, const int* off_x, int ntaps, int in_stride, int Cc, int N, int Hc, int Wc, int three, bool part_of_set);
 bool nhwc_prefers_thin();
+void nhwc_debug_plan(const int* off_y, const int* off_x, int ntaps, int in_stride, int Cc, int N, int B, int Hc, int Wc, bool part_of_set,
+                     int* out16);
 long long nhwc_copy_floats(int B, int Cc, int Hin, int Win);
 long long nhwc_wp_floats(const int* off_y, const int* off_x, int ntaps, int Cc, int N);
 int nhwc_transpose(const float* x, float* xh, int B, int Cc, int Hin, int Win, cudaStream_t st);
@@ -1709,6 +1711,8 @@ int tma_wgrad(const ccb_conv_desc* d, const float* x, const float* dy, float* dw
 //   op FPROP / DGRAD (parity class py, px): out = {kind, cs, cblocks, kt_full, ktiles, SW, SH, slab_bytes, nslab, nstages,
 //       nbox, smem, mt, ntaps, span_x, span_y}   kind: 2 slab, 3 aligned per-tap TMA, 4 direct (then cs = CC, cblocks = nchunks,
 //       kt_full = NG, ktiles = TH, nbox = n8, mt = n-blocks), -1 no tiling
+//   op 16 + FPROP / 16 + DGRAD: out = {6 / -1, cblocks, SH, SW, mt, slab_bytes, slab_tx, nslab, nstages, nbox, ntile_w, tmem_cols, smem, Kp,
+//       span_x << 16 | span_y, CTAs}: the channels-last kernel's tiling (conv_nhwc.cu) when the shape qualifies
 //   op WGRAD: out = {kind 5 / -1, cwid, cblocks, tpt, tgroups, SW, SH, slab_bytes, 1, nstages, nbox, smem, splits, KK, dx0, stages}
 extern "C" int ccb_debug_conv_plan(const ccb_conv_desc* d, int op, int py, int px, int* out16) {
     using namespace ccb;
@@ -1727,6 +1731,25 @@ extern "C" int ccb_debug_conv_plan(const ccb_conv_desc* d, int op, int py, int p
     int oy[TM_MAX_SLOTS], ox[TM_MAX_SLOTS], tix[TM_MAX_SLOTS];
     int nt, in_stride, Cc, N;
     long long out_px;
+    if (op >= 16) {                                              // 16 + FPROP / DGRAD: the channels-last plan of this gather (kind 6) or -1
+        const int s = d->stride;
+        if (op - 16 == CCB_CONV_FPROP) {
+            nt = fprop_taps(d, oy, ox, tix);
+            nhwc_debug_plan(oy, ox, nt, d->stride, d->Ci, d->Co, d->B, d->Ho, d->Wo, false, out16);
+        } else {
+            nt = dgrad_taps(d, py, px, oy, ox, tix);
+            if (nt < 1) { out16[0] = -1; return CCB_OK; }
+            nhwc_debug_plan(oy, ox, nt, 1, d->Co, d->Ci, d->B, (d->Hi - py + s - 1) / s, (d->Wi - px + s - 1) / s, s > 1, out16);
+        }
+        int sx = 0, sy = 0;
+        for (int t = 0; t < nt; ++t)
+            for (int u = 0; u < nt; ++u) {
+                if (ox[t] - ox[u] > sx) sx = ox[t] - ox[u];
+                if (oy[t] - oy[u] > sy) sy = oy[t] - oy[u];
+            }
+        if (out16[0] == 6) { out16[14] = sx * 65536 + sy; }      // spans replace Cp (the test derives Cp itself)
+        return CCB_OK;
+    }
     if (op == CCB_CONV_FPROP) {
         nt = fprop_taps(d, oy, ox, tix); in_stride = d->stride; Cc = d->Ci; N = d->Co;
         out_px = (long long)d->B * d->Ho * d->Wo;

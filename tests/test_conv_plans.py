@@ -115,3 +115,35 @@ def test_plans_cover_the_problem():
         else:
             assert v[0] == -1
     assert {2, 3, 4} <= kinds            # the sweep reaches the slab, the aligned and the direct kernels
+
+
+def test_channels_last_plans():
+    """The channels-last slab kernel's tiling (conv_nhwc.cu) over the same sweep: slab geometry, shared-memory / TMEM
+    budgets of the one- and two-CTA-per-SM configurations, TMA box limits, K coverage."""
+    lib, L = _lib()
+    taken = 0
+    for shp in NET_SHAPES + _random_shapes(300, seed=5):
+        B, Ci, H, W, Co, k, s, p = shp
+        d = _desc(L, *shp)
+        cases = [(16 + FPROP, 0, 0, Ci, Co)] if s == 1 else []
+        cases += [(16 + DGRAD, py, px, Co, Ci) for py, px in itertools.product(range(min(s, H)), range(min(s, W)))]
+        for op, py, px, Cc, N in cases:
+            v = _plan(lib, d, op, py, px)
+            if v[0] != 6:
+                assert v[0] == -1
+                continue
+            taken += 1
+            what = (op, py, px, shp)
+            _, cblocks, SH, SW, mt, slab_bytes, slab_tx, nslab, nst, nbox, ntile_w, tmem_cols, smem, Kp, spans, ctas = v
+            sx, sy = spans >> 16, spans & 0xFFFF
+            assert Cc >= 32 and N >= 16 and cblocks * 32 >= Cc > (cblocks - 1) * 32, what
+            assert SW == 8 + sx <= 16 and SH == 16 * mt + sy <= 256, what            # TMA box (32 ch, SW px, SH rows)
+            assert slab_tx == SH * SW * 128 and slab_bytes >= slab_tx and slab_bytes % 1024 == 0, what
+            assert ntile_w in (64, 128) and tmem_cols == (256 if ntile_w == 64 else 512), what
+            assert nbox % 16 == 0 and min(N, ntile_w) <= nbox <= ntile_w and mt * 3 * nbox <= tmem_cols, what
+            assert 1 <= mt <= 4 and nslab in (1, 2) and (nslab == 1 or cblocks > 1), what
+            assert 2 <= nst <= 8 and (nst >= 3 or ntile_w == 128), what
+            assert smem == 2 * nslab * slab_bytes + nst * 2 * nbox * 128 + 3072, what
+            assert smem <= (113 * 1024 if ntile_w == 64 else SMEM_MAX), what            # two CTAs per SM need <= half the SM
+            assert Kp % 32 == 0 and Kp >= cblocks * 32 and ctas >= 1, what
+    assert taken > 100

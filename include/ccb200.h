@@ -4,7 +4,9 @@
  * Conventions:
  *   - every pointer is a DEVICE pointer to contiguous fp32 NCHW data unless a comment says "host";
  *   - the caller (torch.empty on the Python side) owns every buffer, including workspaces and the
- *     buffers saved for backward; the library owns no tensors and keeps no global mutable state
+ *     buffers saved for backward; the library owns no tensors and keeps no state between calls (the only process-wide
+ *     variables are the launch counter and the bring-up switches of ccb200_debug.h; a weight cache is an explicit handle
+ *     the caller creates, passes in ccb_conv_desc and destroys)
  *     (the reference caches a module-global pixel grid, inverse_warp.py:10 - we do not);
  *   - every entry point is asynchronous on `stream` (a cudaStream_t), never synchronises the host,
  *     never throws, and returns CCB_OK or a negative ccb_status; ccb_last_error_string() explains it;

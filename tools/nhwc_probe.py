@@ -37,6 +37,10 @@ CASES = [  # B, Ci, H, W, Co, k, s, p
     (4, 32, 128, 416, 16, 3, 1, 1),
     (4, 32, 64, 208, 64, 3, 2, 1),        # 21: stride 2: dgrad classes
     (4, 16, 128, 416, 32, 3, 2, 1),
+    (4, 512, 8, 26, 512, 3, 1, 1),        # 23: small maps (need CCB_NHWC_MINH=8 CCB_NHWC_WASTE10=30 to reach the kernel)
+    (4, 1024, 8, 26, 512, 3, 1, 1),
+    (4, 256, 8, 26, 256, 3, 1, 1),
+    (4, 128, 8, 26, 128, 3, 1, 1),
 ]
 
 
@@ -98,7 +102,7 @@ def run_case(i):
         return e0.elapsed_time(e1) / 20 * 1e3
     gflop = 2.0 * B * zd.shape[2] * zd.shape[3] * Co * Ci * k * k / 1e9
     gy = wt
-    for name, on, dbg in (('auto', 1, 0), ('wg_nhwc', 1, 128), ('nchw', 0, 0)):
+    for name, on, dbg in (('auto', 1, 0), ('nchw', 0, 0)):
         lib.ccb_debug_nhwc(on, 1, dbg)
         with torch.no_grad():
             tf = timed(lambda: cnn.conv2d(x, w, b, None, s, p, 'relu', 0.0))

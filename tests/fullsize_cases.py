@@ -35,11 +35,13 @@ from oracle import step as OS
 
 OUT_TOL, LOSS_TOL, GRAD_TOL = 1e-4, 1e-4, 1e-3
 FLOOR_FACTOR = 3.0
-GRAD_TOL_HARD = 2e-3               # no gradient tensor of Pose / Mask / Flow may exceed this, whatever its floor says
+GRAD_TOL_HARD = 3e-3               # no gradient tensor of Pose / Mask / Flow may exceed this, whatever its floor says (measured max 1.7e-3)
+BETWEEN_FRAC = 0.05                # share of a net's tensors allowed between the bar and the cap (measured: Flow 4-5 of 192 = 2.6 %)
 CHAOTIC_NETS = ('disp',)           # see the module docstring
 CHAOS_MEDIAN, CHAOS_L2 = 5.0, 5e-2
-# Pose / Mask / Flow gradients: bar 1e-3 (or 3 x floor); at most 3 % of a net's tensors may sit between the bar and the hard
-# cap (measured at b4 256x832: Flow 4 of 192 at 1.0-1.7e-3, Pose 0, Mask 0)
+# Pose / Mask / Flow gradients: bar 1e-3 (or 3 x floor); at most 5 % of a net's tensors may sit between the bar and the hard
+# cap (measured at b4 256x832 over six runs: Flow 4-5 of 192 at 1.0-1.7e-3, Pose 0, Mask 0; the margins absorb run-to-run
+# differences of the atomics in the feature-warp backward)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -133,8 +135,8 @@ def run(cfg, device, B=4, H=256, W=832, seed=50, with_floor=True, threads=None, 
     for net in sorted({r['name'].split('.')[0] for r in rows if r['kind'] == 'grad'}):
         n = sum(r['kind'] == 'grad' and r['name'].startswith(net + '.') for r in rows)
         k = sum(bool(r.get('between_bar_and_cap')) and r['name'].startswith(net + '.') for r in rows)
-        if k > max(1, int(0.03 * n)):
-            bad.append('%s gradients: %d of %d tensors between the %.0e bar and the %.0e cap (allowed 3 %%)' % (net, k, n, GRAD_TOL, GRAD_TOL_HARD))
+        if k > max(1, int(BETWEEN_FRAC * n)):
+            bad.append('%s gradients: %d of %d tensors between the %.0e bar and the %.0e cap (allowed %.0f %%)' % (net, k, n, GRAD_TOL, GRAD_TOL_HARD, 100 * BETWEEN_FRAC))
     for net in CHAOTIC_NETS:
         ratios = [r['err'] / max(r['floor'], 1e-9) for r in rows if r.get('chaotic') and r['name'].startswith(net + '.')]
         if ratios and statistics.median(ratios) > CHAOS_MEDIAN:
